@@ -1,0 +1,197 @@
+/*
+ * mcts.h -- C ABI of libmcts.so, the B200 (sm_100a) Monte Carlo path-simulation
+ * core that replaces the hot path of jensbrodersen/mc-trade-sizing:
+ *
+ *     run_all_strategies()            src/trading_models.py:445-530
+ *       simulate_trades_dynamic       src/trading_models.py:43-66
+ *       simulate_trades_markov        src/trading_models.py:68-85
+ *       simulate_trades_markov2       src/trading_models.py:87-104
+ *       simulate_trades_regime_switch src/trading_models.py:106-128
+ *       np.random.shuffle per path    src/trading_models.py:491-492
+ *       strategy_static / _dynamic    src/trading_models.py:135-168
+ *       make_condition_func (20 ids)  src/trading_models.py:170-404
+ *       calculate_drawdown            src/trading_models.py:130-133
+ *       per-strategy aggregates       src/trading_models.py:509-522
+ *
+ * The reference is pure Python and has no FFI; the binding a maintainer adds is
+ * the ctypes stub in INTEGRATION.md (shipped as mc_trade_sizing_b200/_ffi.py).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative mcts_status; the
+ *     message is available from mcts_last_error() (thread-local);
+ *   - the caller allocates every output buffer; the library never keeps a
+ *     caller pointer after the call returns; all pointers are HOST pointers
+ *     unless a parameter says "device";
+ *   - there is no CPU fallback: without a usable CUDA device mcts_create fails;
+ *   - a handle is bound to one device and must not be used concurrently from
+ *     two threads; distinct handles (and distinct processes) are independent.
+ */
+#ifndef MCTS_H
+#define MCTS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCTS_NSTRAT 20
+#define MCTS_MAX_REGIMES 16
+#define MCTS_ABI_VERSION 1
+
+typedef enum {
+    MCTS_OK = 0,
+    MCTS_EINVAL = -1,     /* invalid argument (NumPy would raise ValueError: bad probabilities ...) */
+    MCTS_EEMPTY = -2,     /* zero paths or an empty trade sequence (np.min([]) raises in the reference) */
+    MCTS_ENOMEM = -3,     /* host or device allocation failed */
+    MCTS_ECUDA = -4,      /* CUDA runtime error, message has the details */
+    MCTS_ENODEVICE = -5,  /* no usable CUDA device / wrong architecture: there is no CPU fallback */
+    MCTS_EUNSUPPORTED = -6 /* valid for the reference but outside this build's limits (see message) */
+} mcts_status;
+
+/* Generator selection, same precedence as trading_models.py:477-490. */
+typedef enum {
+    MCTS_MODE_DYNAMIC = 0, /* "No Markov": simulate_trades_dynamic, :43-66 */
+    MCTS_MODE_MARKOV1 = 1, /* simulate_trades_markov, :68-85 */
+    MCTS_MODE_MARKOV2 = 2, /* simulate_trades_markov2, :87-104 */
+    MCTS_MODE_REGIME = 3   /* simulate_trades_regime_switch, :106-128 */
+} mcts_mode;
+
+typedef struct {
+    int32_t length;
+    double hit_rate, avg_win, avg_loss;
+} mcts_regime;
+
+/* The argument list of run_all_strategies (:445-450), flattened. */
+typedef struct {
+    int32_t mode; /* mcts_mode */
+    int32_t num_trades;
+    int32_t num_simulations;
+    int32_t num_mc_shuffles;
+    double hit_rate, avg_win, avg_loss;
+    double p_win_after_win, p_win_after_loss;
+    double p_win_ww, p_win_wl, p_win_lw, p_win_ll;
+    int32_t n_regimes; /* < 0: regimes=None, the defaults of :108-112 */
+    mcts_regime regimes[MCTS_MAX_REGIMES];
+} mcts_params;
+
+/* Per-strategy aggregate over paths (:513-518). sum_* follow np.mean's pairwise
+ * summation order over the path index (sim-major, shuffle-minor, :507), so
+ * sum_profit / count reproduces np.mean bit for bit. */
+typedef struct {
+    double sum_profit, sum_dd;
+    double min_profit, max_profit;
+    double min_dd, max_dd; /* min_dd = most negative, max_dd = least negative (:517-518) */
+    int64_t count;
+} mcts_agg;
+
+typedef struct {
+    int64_t chunk_paths;   /* max paths per device chunk (0 = default 1<<22); chunks are nodes of
+                              NumPy's pairwise-summation tree so partial sums combine exactly */
+    int32_t dedup;         /* 0 = evaluate all 20 state machines (default); 1 = evaluate the 11
+                              distinct behaviours once and fan the results out (identical output) */
+    int32_t int_fast_path; /* 0 = fp64 evaluator always; 1 = allow the exact int32 evaluator when
+                              every trade value is an integer and sums stay below 2^31 */
+    int32_t block_threads; /* 0 = default */
+    int32_t reserved;
+} mcts_options;
+
+/* Device-side timing of the last call on a handle (CUDA events on the library's stream). */
+typedef struct {
+    double total_ms;    /* first launch .. last kernel of the call */
+    double gen_ms;      /* base multiset generation (per simulation) */
+    double paths_ms;    /* the dominant kernel: shuffle + 20 strategies per path */
+    double reduce_ms;   /* exact-order pairwise reduction of per-path results */
+    int64_t launches;   /* kernels launched by the call */
+    int64_t paths_launches;
+    int64_t trade_steps; /* paths x trades x 20 */
+    int64_t h2d_bytes, d2h_bytes;
+} mcts_timing;
+
+/* One node of the pairwise tree over paths, evaluated on one device (multi-GPU exchange record). */
+typedef struct {
+    int64_t first_path, n_paths;
+    double sum_profit[MCTS_NSTRAT], sum_dd[MCTS_NSTRAT];
+    double min_profit[MCTS_NSTRAT], max_profit[MCTS_NSTRAT];
+    double min_dd[MCTS_NSTRAT], max_dd[MCTS_NSTRAT];
+} mcts_chunk_result;
+
+typedef struct mcts_handle mcts_handle;
+
+int mcts_abi_version(void);
+const char *mcts_last_error(void);
+
+/* Bind a handle to CUDA device `device` (>= 0). Fails with MCTS_ENODEVICE if the device is
+ * absent or is not compute capability 10.x. */
+int mcts_create(int device, mcts_handle **out);
+void mcts_destroy(mcts_handle *h);
+
+/* Length of the trade sequence the selected generator yields (not always num_trades:
+ * Markov-2 emits >= 2 trades, regime lists can be short; :89-91, :116-126). */
+int64_t mcts_sequence_length(const mcts_params *p);
+
+/*
+ * run_all_strategies with on-device RNG (replaces :476-522).
+ *   seed      Philox4x32-10 key; draws are keyed by (simulation, shuffle, trade), so results
+ *             do not depend on chunking or on how paths are split over devices
+ *   agg       [20] aggregates in strategy-id order (id 1 first)
+ *   profit,dd optional [20][P] per-path results, P = num_simulations*num_mc_shuffles (NULL to skip)
+ */
+int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt,
+                  mcts_agg *agg, double *profit, double *dd);
+
+/*
+ * Replay: evaluate caller-supplied post-shuffle sequences (replaces :493-507 + :509-518).
+ *   values    [P][T] row-major trade results (what np.random.shuffle left in base_results)
+ *   profit,dd optional [20][P]
+ */
+int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt,
+                mcts_agg *agg, double *profit, double *dd);
+
+/* The post-shuffle sequences the device generator produces for paths [first_path, first_path+n),
+ * as doubles [n][L], L = mcts_sequence_length(p).  Test / audit hook: feeding these to the
+ * reference evaluator must reproduce mcts_simulate's per-path results bit for bit. */
+int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n,
+                   double *values);
+
+/* --- multi-device: paths shard by pairwise-tree node ------------------------------------- */
+
+/* Number of chunks the path range [0,P) splits into for a given chunk size. */
+int64_t mcts_plan_count(int64_t P, int64_t chunk_paths);
+/* first_path/n_paths of every chunk, in path order. */
+int mcts_plan(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_paths);
+/* Evaluate chunks [chunk_begin, chunk_end) of the plan on this handle's device. */
+int mcts_simulate_chunks(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt,
+                         int64_t chunk_begin, int64_t chunk_end, mcts_chunk_result *out);
+/* Combine the results of ALL chunks of the plan (any device order, sorted here by first_path)
+ * in NumPy's tree order.  Pure host arithmetic on ~1 KB records. */
+int mcts_combine(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks,
+                 mcts_agg *agg);
+
+/* --- equity-curve export (extension; the reference only has the temporary of :167) -------- */
+
+/* Equity curves of paths [first_path, first_path+n) for all 20 strategies written to DEVICE memory
+ * `curves_dev` as [20][ceil(L/2)][n][2] doubles (two trades per 128-bit store, paths contiguous).
+ * Returns the achieved device bandwidth through mcts_get_timing (paths_ms). */
+int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n,
+                       double *curves_dev);
+void *mcts_device_alloc(mcts_handle *h, int64_t bytes);
+void mcts_device_free(mcts_handle *h, void *ptr);
+int mcts_copy_to_host(mcts_handle *h, void *dst_host, const void *src_dev, int64_t bytes);
+
+/* --- result-table arithmetic of :513-521 (ratios, inf rules), strategy-id order ----------- */
+/* rows[20][9] = avg_profit, avg_drawdown, ratio, min_profit, max_profit, min_dd, max_dd,
+ *               avg_per_trade, ratio_max_dd */
+int mcts_summary_rows(const mcts_agg *agg, int32_t num_trades, double *rows);
+
+/* --- measurement ---------------------------------------------------------------------------- */
+int mcts_get_timing(const mcts_handle *h, mcts_timing *out);
+/* Issue-rate microbenchmarks used as roofline denominators: independent DADD chains
+ * and independent IADD3/LOP3 chains over the whole chip. Results in warp-wide... thread-level
+ * instructions per second. */
+int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCTS_H */

@@ -1,0 +1,367 @@
+// eval_core.cuh -- the per-path evaluator: position-sizing rules, equity / peak / drawdown and the
+// NumPy-ordered profit sum, written once for device code and (for CPU unit tests of the very same
+// code, never as a fallback) for the host.
+//
+// Reference semantics (src/trading_models.py):
+//   strategy_dynamic  :141-168   contribution c_t = value_t * size (0 while paused), host streak
+//                                update, closure returns the NEXT size
+//   make_condition_func :170-404 the 20 closures.  Because the host loop and many closures both
+//                                bump the same streak counters, every one of them reduces to a
+//                                function of the previous TWO outcomes only (verified
+//                                against the literal closures by tests/test_eval_core_cpu.py and the
+//                                GPU replay parity tests).
+//   np.cumsum :167 / :136        equity: strictly sequential fp64 adds
+//   np.sum    :168 / :137        profit: pairwise tree, 8 interleaved accumulators per <=128 leaf
+//   calculate_drawdown :130-133  min_t (E_t - max_{j<=t} E_j), peak starts at E_0
+//
+// No multiply-add contraction can occur here: the categorical path only adds (products v*1, v*2,
+// v*3 are tabulated on the host), the replay path uses __dmul_rn.
+#pragma once
+#include <stdint.h>
+
+#include <utility>
+
+#include "spec.hpp"
+
+namespace mcts {
+
+// ---- the 11 distinct behaviours of the 20 strategy ids -------------------------
+enum Rule : int {
+    R_C1 = 0,  // ids 1, 3          always size 1
+    R_AM,      // ids 2, 13         2 after a win
+    R_F1,      // ids 4, 5, 14, 17  2 after the first win of a run only
+    R_MG,      // ids 6, 7          2 after a loss
+    R_MG2,     // id 8              2 after >= 2 consecutive losses
+    R_P1,      // ids 9, 10, 15     pause after a win until a loss has passed
+    R_P2,      // ids 11, 12        pause after 2 consecutive wins until a loss has passed
+    R_S16,     // id 16             win -> pause; loss while trading -> 2; loss ending a pause -> 1
+    R_S18,     // id 18             3 after >= 2 consecutive wins
+    R_S19,     // id 19             2 after >= 2 wins, 3 after >= 2 losses
+    R_S20      // id 20             3 after >= 2 consecutive losses
+};
+
+MCTS_HD constexpr int rule_of_id(int id)
+{
+    constexpr int t[21] = {-1, R_C1, R_AM, R_C1, R_F1, R_F1, R_MG, R_MG, R_MG2, R_P1, R_P1,
+                           R_P2, R_P2, R_AM, R_F1, R_P1, R_S16, R_F1, R_S18, R_S19, R_S20};
+    return t[id];
+}
+
+template <int... IDS>
+struct IdList {
+    static constexpr int N = sizeof...(IDS);
+    MCTS_HD static constexpr int id(int i)
+    {
+        constexpr int a[N] = {IDS...};
+        return a[i];
+    }
+};
+
+// all 20 state machines, five per pass; no two ids of one behaviour class share a pass, so every
+// id carries its own equity / peak / drawdown / profit chain
+using FullPass0 = IdList<1, 2, 4, 6, 9>;
+using FullPass1 = IdList<3, 13, 5, 7, 10>;
+using FullPass2 = IdList<14, 15, 11, 8, 16>;
+using FullPass3 = IdList<17, 12, 18, 19, 20>;
+// one representative per behaviour class (results fanned out by the caller)
+using DedupPass0 = IdList<1, 2, 4, 6>;
+using DedupPass1 = IdList<8, 9, 11, 16>;
+using DedupPass2 = IdList<18, 19, 20>;
+
+template <int N, class F, int... Is>
+MCTS_HD void static_for_impl(F &&f, std::integer_sequence<int, Is...>)
+{
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+MCTS_HD void static_for(F &&f)
+{
+    static_for_impl<N>(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// Outcome-history masks of one 8-trade block.  Bit 4*i of a mask is the predicate for trade i:
+//   pw  previous trade won          pl  previous trade lost
+//   pww previous two both won       pll previous two both lost
+//   fw  previous won, the one before did not (first win of a run; also true at the 2nd trade)
+//   s16 previous lost and the one before did not win
+// "lost" means "existed and value <= 0": before the first trade nothing won and nothing lost.
+struct Masks {
+    uint32_t pw, pl, pww, pll, fw, s16;
+};
+
+struct History {
+    uint32_t w, l;  // win / loss bits of the previous block (nibble LSBs)
+};
+
+MCTS_HD Masks make_masks(uint32_t W, uint32_t Lb, History &h)
+{
+    Masks m;
+    const uint32_t pw = (W << 4) | (h.w >> 28), ppw = (W << 8) | (h.w >> 24);
+    const uint32_t pl = (Lb << 4) | (h.l >> 28), ppl = (Lb << 8) | (h.l >> 24);
+    m.pw = pw;
+    m.pl = pl;
+    m.pww = pw & ppw;
+    m.pll = pl & ppl;
+    m.fw = pw & ~ppw;
+    m.s16 = pl & ~ppw;
+    h.w = W;
+    h.l = Lb;
+    return m;
+}
+
+// contribution of the current trade for one behaviour: a select among {0, v, 2v, fl(3v)}
+template <int RULE>
+MCTS_HD double contribution(const Masks &m, uint32_t bit, double v1, double v2, double v3)
+{
+    if constexpr (RULE == R_C1) return v1;
+    if constexpr (RULE == R_AM) return (m.pw & bit) ? v2 : v1;
+    if constexpr (RULE == R_F1) return (m.fw & bit) ? v2 : v1;
+    if constexpr (RULE == R_MG) return (m.pl & bit) ? v2 : v1;
+    if constexpr (RULE == R_MG2) return (m.pll & bit) ? v2 : v1;
+    if constexpr (RULE == R_P1) return (m.pw & bit) ? 0.0 : v1;
+    if constexpr (RULE == R_P2) return (m.pww & bit) ? 0.0 : v1;
+    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0.0 : ((m.s16 & bit) ? v2 : v1);
+    if constexpr (RULE == R_S18) return (m.pww & bit) ? v3 : v1;
+    if constexpr (RULE == R_S19) return (m.pww & bit) ? v2 : ((m.pll & bit) ? v3 : v1);
+    if constexpr (RULE == R_S20) return (m.pll & bit) ? v3 : v1;
+    return v1;
+}
+
+MCTS_HD double neg_zero() { return -0.0; }
+MCTS_HD double neg_inf()
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0xfff0000000000000ll);
+#else
+    return -__builtin_inf();
+#endif
+}
+
+// Running state of NS strategies on one path.
+template <int NS>
+struct Acc {
+    double E[NS];     // equity (np.cumsum, sequential)
+    double peak[NS];  // np.maximum.accumulate
+    double dd[NS];    // np.min(equity - peak)
+    double r[NS][8];  // the 8 interleaved accumulators of the current pairwise leaf
+    History h;
+};
+
+template <int NS>
+MCTS_HD void acc_init(Acc<NS> &a)
+{
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        a.E[s] = neg_zero();  // -0.0 + c == c bit for bit, so E_0 = c_0 needs no special case
+        a.peak[s] = neg_inf();  // first trade: u = +inf > 0 -> peak_0 = E_0, d_0 = +0.0
+        a.dd[s] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.r[s][j] = neg_zero();  // leaf starts with r[j] = a[j]
+    }
+    a.h.w = 0;
+    a.h.l = 0;
+}
+
+// one trade of one strategy:  E += c;  r_j += c;  u = E - peak_old;  peak = max;  dd = min(dd, u)
+// (u <= 0 is exactly the reference's E_t - peak_t; when u > 0 the reference records +0.0, which
+// never lowers dd because dd <= 0 from the first trade on)
+MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double c)
+{
+    E = E + c;
+    rj = rj + c;
+    const double u = E - peak;
+    peak = (u > 0.0) ? E : peak;
+    dd = (u < dd) ? u : dd;
+}
+
+// A full block of 8 trades.  SRC provides, per trade i, the three tabulated contributions.
+// SINK receives the equity of every (strategy slot, trade) when curves are exported.
+struct NoSink {
+    template <int S>
+    MCTS_HD void put(int, double)
+    {
+    }
+};
+
+template <class IDS, class SRC, class SINK>
+MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t0)
+{
+    const Masks m = make_masks(W, W ^ 0x11111111u, a.h);
+    static_for<8>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        double v1, v2, v3;
+        src.template get<i>(v1, v2, v3);
+        constexpr uint32_t bit = 1u << (4 * i);
+        static_for<IDS::N>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            constexpr int rule = rule_of_id(IDS::id(s));
+            const double c = contribution<rule>(m, bit, v1, v2, v3);
+            trade_step(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
+            sink.template put<s>(t0 + i, a.E[s]);
+        });
+    });
+}
+
+// The < 8 trades after the last full block: added one by one to the leaf result (the n % 8 loop
+// of the pairwise leaf, or the whole n < 8 case).  W/Lb bits beyond `count` are ignored.
+template <class IDS, class SRC, class SINK>
+MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32_t Lb, int count, SRC &src, SINK &sink, int t0)
+{
+    const Masks m = make_masks(W, Lb, a.h);
+    for (int i = 0; i < count; i++) {
+        double v1, v2, v3;
+        src.get_dyn(i, v1, v2, v3);
+        const uint32_t bit = 1u << (4 * i);
+        static_for<IDS::N>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            constexpr int rule = rule_of_id(IDS::id(s));
+            const double c = contribution<rule>(m, bit, v1, v2, v3);
+            trade_step(a.E[s], a.peak[s], a.dd[s], res[s], c);
+            sink.template put<s>(t0 + i, a.E[s]);
+        });
+    }
+}
+
+// Evaluate the strategies of one pass over a whole path.
+//   SRC: uint32_t load(int oct)       -> win bits of block `oct` (and latches its values)
+//        uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
+//        get<i>() / get_dyn(i)
+template <class IDS, class SRC, class SINK>
+MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, double (&profit)[IDS::N], double (&drawdown)[IDS::N])
+{
+    constexpr int NS = IDS::N;
+    Acc<NS> a;
+    acc_init(a);
+    double stk[NS][kMaxStackDepth];
+    double res[NS];
+    int sp = 0;
+    int oct = 0;
+    const int n_leaves = sch->n_leaves;
+    for (int leaf = 0; leaf < n_leaves; leaf++) {
+        const int end = sch->end_oct[leaf];
+        const bool has_blocks = oct < end;
+        for (; oct < end; oct++) {
+            const uint32_t W = src.load(oct);
+            eval_block8<IDS>(a, W, src, sink, oct * 8);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            // leaf result: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); a leaf without a full block starts from 0.
+            res[s] = has_blocks ? ((a.r[s][0] + a.r[s][1]) + (a.r[s][2] + a.r[s][3])) + ((a.r[s][4] + a.r[s][5]) + (a.r[s][6] + a.r[s][7])) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) a.r[s][j] = neg_zero();
+        }
+        if (leaf == n_leaves - 1 && sch->tail > 0) {
+            uint32_t Lb;
+            const uint32_t W = src.load_tail(oct, sch->tail, &Lb);
+            eval_tail<IDS>(a, res, W, Lb, sch->tail, src, sink, oct * 8);
+        }
+        int merges = sch->merges[leaf];
+#pragma unroll
+        for (int s = 0; s < NS; s++) stk[s][sp] = res[s];
+        sp++;
+        for (; merges > 0; merges--) {
+            sp--;
+#pragma unroll
+            for (int s = 0; s < NS; s++) stk[s][sp - 1] = stk[s][sp - 1] + stk[s][sp];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        profit[s] = 0.0 + stk[s][0];  // np.add.reduce starts from the identity 0.0
+        drawdown[s] = a.dd[s];
+    }
+}
+
+// ---- value sources ----------------------------------------------------------------------------
+
+// categorical: 8 trades per 32-bit word, 4-bit code each; code -> {v, 2v, fl(3v)} table
+struct CodeSource {
+    const uint32_t *codes;  // word of block `oct` at codes[oct * stride]
+    int stride;
+    const Tab *tab;
+    uint32_t word;
+    MCTS_HD uint32_t load(int oct)
+    {
+        word = codes[(size_t)oct * stride];
+        return word & 0x11111111u;
+    }
+    MCTS_HD uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
+    {
+        word = codes[(size_t)oct * stride];
+        const uint32_t valid = count >= 8 ? 0x11111111u : (0x11111111u & ((1u << (4 * count)) - 1u));
+        const uint32_t W = word & valid;
+        *loss_bits = W ^ valid;
+        return W;
+    }
+    template <int I>
+    MCTS_HD void get(double &v1, double &v2, double &v3) const
+    {
+        const Tab &t = tab[(word >> (4 * I)) & 15u];
+        v1 = t.v1;
+        v2 = t.v2;
+        v3 = t.v3;
+    }
+    MCTS_HD void get_dyn(int i, double &v1, double &v2, double &v3) const
+    {
+        const Tab &t = tab[(word >> (4 * i)) & 15u];
+        v1 = t.v1;
+        v2 = t.v2;
+        v3 = t.v3;
+    }
+};
+
+MCTS_HD double mul_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;  // host harness is compiled with -ffp-contract=off
+#endif
+}
+
+// replay: arbitrary fp64 trade results of one path, contiguous in memory
+struct ValueSource {
+    const double *row;
+    double v[8];
+    MCTS_HD uint32_t load(int oct)
+    {
+        uint32_t W = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = row[oct * 8 + i];
+            W |= (v[i] > 0.0 ? 1u : 0u) << (4 * i);  // win <=> value > 0 (:154)
+        }
+        return W;
+    }
+    MCTS_HD uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
+    {
+        uint32_t W = 0, V = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = i < count ? row[oct * 8 + i] : 0.0;
+            W |= ((i < count && v[i] > 0.0) ? 1u : 0u) << (4 * i);
+            V |= (i < count ? 1u : 0u) << (4 * i);
+        }
+        *loss_bits = W ^ V;
+        return W;
+    }
+    template <int I>
+    MCTS_HD void get(double &v1, double &v2, double &v3) const
+    {
+        v1 = v[I];
+        v2 = mul_rn(v[I], 2.0);
+        v3 = mul_rn(v[I], 3.0);
+    }
+    MCTS_HD void get_dyn(int i, double &v1, double &v2, double &v3) const
+    {
+        double x = v[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) x = (i == j) ? v[j] : x;
+        v1 = x;
+        v2 = mul_rn(x, 2.0);
+        v3 = mul_rn(x, 3.0);
+    }
+};
+
+}  // namespace mcts

@@ -1,0 +1,194 @@
+// gen_core.cuh -- counter-based trade-outcome generation (host/device, same code).
+//
+// Replaces NumPy's global MT19937 stream of the reference (RNG call sites
+// src/trading_models.py:55,65,70,77,79,89,101,119,492) by Philox4x32-10 keyed with the user seed
+// and countered by (simulation, shuffle, trade), so any path can be regenerated anywhere:
+//
+//   base multiset of simulation `sim` (generators :43-128): uniform #i is the 53-bit integer built
+//       from words (2*(i%2), 2*(i%2)+1) of Philox(ctr = (i/2, 0, sim, 0)); win <=> integer < thr,
+//       thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).
+//       Only the per-category COUNTS survive, because the reference shuffles every sequence before
+//       using it (:491-492) and a shuffled sequence is a uniform permutation of its multiset.
+//   path (sim, k), trade t (the np.random.shuffle of :492): the next trade is drawn from the urn of
+//       remaining counts, category = first r with idx < C_r, idx = mulhi32(x, remaining),
+//       x = word (t%4) of Philox(ctr = (t/4, k, sim, 1)).  Sequential urn draws generate a uniform
+//       permutation of the multiset, exactly the distribution Fisher-Yates gives; the multiply-shift
+//       index has bias <= remaining / 2^32 (< 2.4e-7 for 1000 trades).
+#pragma once
+#include <stdint.h>
+
+#include "spec.hpp"
+
+namespace mcts {
+
+MCTS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); constants as in Random123 / cuRAND.
+MCTS_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4])
+{
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+constexpr uint32_t kStreamBase = 0u, kStreamShuffle = 1u;
+
+// sequential reader of the 53-bit uniforms of one simulation's base stream
+struct BaseStream {
+    uint32_t k0, k1, sim;
+    uint32_t i;
+    uint32_t x[4];
+    MCTS_HD void init(uint64_t seed, uint32_t sim_)
+    {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32);
+        sim = sim_;
+        i = 0;
+    }
+    MCTS_HD uint64_t next()
+    {
+        if ((i & 1u) == 0u) philox4x32_10(k0, k1, i >> 1, 0u, sim, kStreamBase, x);
+        const uint32_t a = (i & 1u) ? x[2] : x[0], b = (i & 1u) ? x[3] : x[1];
+        i++;
+        return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+    }
+};
+
+// Per-category counts of the base sequence of one simulation (what :477-490 would have produced).
+MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t (&counts)[kMaxCat])
+{
+#pragma unroll
+    for (int k = 0; k < kMaxCat; k++) counts[k] = 0;
+    BaseStream rs;
+    rs.init(seed, sim);
+    if (g.kind == GEN_SEGMENTS) {
+        for (int s = 0; s < g.n_seg; s++) {
+            const Segment sg = g.seg[s];
+            uint32_t wins = 0;
+            for (int t = 0; t < sg.len; t++) wins += rs.next() < sg.thr ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < kMaxCat; k++) {
+                counts[k] += (k == sg.cat_win ? wins : 0u) + (k == sg.cat_loss ? (uint32_t)sg.len - wins : 0u);
+            }
+        }
+    } else {
+        uint32_t wins = 0;
+        if (g.kind == GEN_MARKOV1) {
+            uint32_t last = rs.next() < g.thr_init ? 1u : 0u;  // :70
+            wins = last;
+            const uint64_t t_l = g.thr1[0], t_w = g.thr1[1];
+            for (int t = 1; t < g.L; t++) {  // :74-84
+                last = rs.next() < (last ? t_w : t_l) ? 1u : 0u;
+                wins += last;
+            }
+        } else {
+            uint32_t older = rs.next() < g.thr_init ? 1u : 0u;  // :89, two unconditional trades
+            uint32_t newer = rs.next() < g.thr_init ? 1u : 0u;
+            wins = older + newer;
+            const uint64_t t_ll = g.thr2[0], t_lw = g.thr2[1], t_wl = g.thr2[2], t_ww = g.thr2[3];
+            for (int t = 2; t < g.L; t++) {  // :92-103
+                const uint64_t thr = older ? (newer ? t_ww : t_wl) : (newer ? t_lw : t_ll);
+                const uint32_t w = rs.next() < thr ? 1u : 0u;
+                wins += w;
+                older = newer;
+                newer = w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxCat; k++) {
+            counts[k] += (k == g.cat_win ? wins : 0u) + (k == g.cat_loss ? (uint32_t)g.L - wins : 0u);
+        }
+    }
+}
+
+// The urn of one path: cumulative remaining counts C_0 <= C_1 <= ... <= C_{K-1} = remaining.
+template <int K>
+struct Urn {
+    uint32_t C[K > 1 ? K - 1 : 1];
+    uint32_t rem;
+    MCTS_HD void init(const uint32_t *counts)
+    {
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            c += counts[j];
+            if (j < K - 1) C[j] = c;
+        }
+        rem = c;
+    }
+    // draw one trade; returns the category rank
+    MCTS_HD uint32_t draw(uint32_t x)
+    {
+        const uint32_t idx = mulhi32(x, rem);
+        uint32_t rank = 0;
+#pragma unroll
+        for (int j = 0; j < K - 1; j++) {
+            const uint32_t lt = idx < C[j] ? 1u : 0u;
+            C[j] -= lt;
+            rank += 1u - lt;
+        }
+        rem -= 1u;
+        return rank;
+    }
+};
+
+// Generate the 4-bit outcome codes of path (sim, k): 8 trades per word, word `oct` stored at
+// codes[oct * stride].  The last word may be partial (upper nibbles 0).
+template <int K>
+MCTS_HD void gen_path_codes(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t k, const uint32_t *counts, uint32_t *codes, int stride)
+{
+    Urn<K> urn;
+    urn.init(counts);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t rank_codes = g.rank_codes;
+    const int n_oct = g.L >> 3, tail = g.L & 7;
+    for (int oct = 0; oct < n_oct; oct++) {
+        uint32_t xa[4], xb[4];
+        philox4x32_10(k0, k1, 2u * oct, k, sim, kStreamShuffle, xa);
+        philox4x32_10(k0, k1, 2u * oct + 1u, k, sim, kStreamShuffle, xb);
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t r = urn.draw(i < 4 ? xa[i] : xb[i - 4]);
+            word |= ((rank_codes >> (4u * r)) & 15u) << (4 * i);
+        }
+        codes[(size_t)oct * stride] = word;
+    }
+    if (tail) {
+        uint32_t xa[4], xb[4];
+        philox4x32_10(k0, k1, 2u * n_oct, k, sim, kStreamShuffle, xa);
+        philox4x32_10(k0, k1, 2u * n_oct + 1u, k, sim, kStreamShuffle, xb);
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i < tail) {
+                const uint32_t r = urn.draw(i < 4 ? xa[i] : xb[i - 4]);
+                word |= ((rank_codes >> (4u * r)) & 15u) << (4 * i);
+            }
+        }
+        codes[(size_t)n_oct * stride] = word;
+    }
+}
+
+}  // namespace mcts

@@ -1,0 +1,285 @@
+// kernels.cuh -- the sm_100a kernels of the path-simulation core.
+//
+//   k_gen_base      one thread per simulation: category counts of the base sequence (generators
+//                   src/trading_models.py:43-128 on Philox uniforms)
+//   k_sim_paths     THE hot kernel, one thread per path (= simulation x shuffle, :491-507):
+//                   urn-draw the shuffled outcome sequence into a thread-private shared-memory
+//                   column (4 bits per trade), then evaluate the 20 strategies in passes of five with
+//                   equity/peak/drawdown/profit accumulators in fp64 registers; per-path results
+//                   go to HBM once (320 B per path = 0.016 B per trade-step)
+//   k_replay_pass   same evaluator on caller-supplied fp64 sequences (replay mode)
+//   k_reduce_*      np.mean-ordered (pairwise) sums + min/max over the paths of a chunk (:513-518)
+//   k_sequences     audit hook: the generated sequences as doubles
+//   k_peak_*        issue-rate microbenchmarks (roofline denominators)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/mcts.h"
+#include "eval_core.cuh"
+#include "gen_core.cuh"
+#include "pairwise.cuh"
+#include "spec.hpp"
+
+namespace mcts {
+
+constexpr int kBlock = 64;         // threads per block of the path kernels (no intra-block cooperation)
+constexpr int kBlocksPerSM = 6;    // 384 threads/SM -> up to 168 registers per thread
+constexpr int kTabWords = 16 * sizeof(Tab) / 4;
+
+enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
+
+struct PathArgs {
+    GenSpec g;
+    uint64_t seed;
+    int64_t path0;  // global index of the first path of this launch
+    int64_t n;      // paths in this launch
+    int64_t sim0;   // first simulation in `counts`
+    int32_t n_sh;   // num_mc_shuffles
+    int32_t pad;
+    const uint32_t *counts;   // [sims][kMaxCat]
+    const LeafSched *sched;
+    double *out;              // [40][ld]: row id-1 = profit, row 20+id-1 = drawdown
+    int64_t ld;
+    double *curves;           // PM_CURVES: [20][ceil(L/2)][n][2]
+};
+
+__global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__ GenSpec g, uint64_t seed, int64_t sim0, int64_t n_sims, uint32_t *__restrict__ counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sims) return;
+    uint32_t c[kMaxCat];
+    gen_base_counts(g, seed, (uint32_t)(sim0 + i), c);
+    uint4 *dst = reinterpret_cast<uint4 *>(counts + i * kMaxCat);
+    dst[0] = make_uint4(c[0], c[1], c[2], c[3]);
+    dst[1] = make_uint4(c[4], c[5], c[6], c[7]);
+}
+
+// equity-curve sink: two consecutive trades per 128-bit store, paths contiguous
+template <class IDS>
+struct CurveSink {
+    double2 *base;    // curves as double2 [20][half][n]
+    int64_t n, local;
+    int32_t half, L;
+    double hold[IDS::N];
+    template <int S>
+    __device__ __forceinline__ void put(int t, double E)
+    {
+        if ((t & 1) == 0) {
+            hold[S] = E;
+            if (t != L - 1) return;
+            E = 0.0;  // odd L: pad the last pair
+            t++;
+        }
+        constexpr int id = IDS::id(S);
+        double2 v = make_double2(hold[S], E);
+        __stcs(base + ((int64_t)(id - 1) * half + (t >> 1)) * n + local, v);
+    }
+};
+
+template <class IDS, int MODE, class SRC>
+__device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t local)
+{
+    double profit[IDS::N], dd[IDS::N];
+    if constexpr (MODE == PM_CURVES) {
+        CurveSink<IDS> sink;
+        sink.base = reinterpret_cast<double2 *>(a.curves);
+        sink.n = a.n;
+        sink.local = local;
+        sink.L = a.g.L;
+        sink.half = (a.g.L + 1) >> 1;
+        eval_path<IDS>(src, sink, a.sched, profit, dd);
+    } else {
+        NoSink sink;
+        eval_path<IDS>(src, sink, a.sched, profit, dd);
+    }
+    if (a.out == nullptr) return;
+    static_for<IDS::N>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        constexpr int id = IDS::id(s);
+        if constexpr (MODE == PM_DEDUP) {
+#pragma unroll
+            for (int other = 1; other <= kNumStrategies; other++) {
+                if (rule_of_id(other) == rule_of_id(id)) {
+                    a.out[(int64_t)(other - 1) * a.ld + local] = profit[s];
+                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + local] = dd[s];
+                }
+            }
+        } else {
+            a.out[(int64_t)(id - 1) * a.ld + local] = profit[s];
+            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + local] = dd[s];
+        }
+    });
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_sim_paths(const __grid_constant__ PathArgs a)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    Tab *tab = reinterpret_cast<Tab *>(smem);
+    uint32_t *codes = smem + kTabWords;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 16 * 4; i += kBlock) reinterpret_cast<double *>(tab)[i] = reinterpret_cast<const double *>(a.g.tab)[i];
+    __syncthreads();
+    const int64_t local = (int64_t)blockIdx.x * kBlock + tid;
+    if (local >= a.n) return;
+    const int64_t path = a.path0 + local;
+    const int64_t sim = path / a.n_sh;
+    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+    uint32_t cnt[kMaxCat];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.counts + (sim - a.sim0) * kMaxCat);
+        const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
+        cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w;
+        cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
+    }
+    // the code column of this thread is private: no barrier between generation and evaluation
+    gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
+    CodeSource src;
+    src.codes = codes + tid;
+    src.stride = kBlock;
+    src.tab = tab;
+    src.word = 0;
+    if constexpr (MODE == PM_DEDUP) {
+        run_pass<DedupPass0, MODE>(src, a, local);
+        run_pass<DedupPass1, MODE>(src, a, local);
+        run_pass<DedupPass2, MODE>(src, a, local);
+    } else {
+        run_pass<FullPass0, MODE>(src, a, local);
+        run_pass<FullPass1, MODE>(src, a, local);
+        run_pass<FullPass2, MODE>(src, a, local);
+        run_pass<FullPass3, MODE>(src, a, local);
+    }
+}
+
+// replay: values [n][T] row-major fp64 in device memory, one pass (five strategies) per launch
+template <class IDS, int MODE>
+__global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __grid_constant__ PathArgs a, const double *__restrict__ values, int64_t T)
+{
+    const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (local >= a.n) return;
+    ValueSource src;
+    src.row = values + local * T;
+    run_pass<IDS, MODE>(src, a, local);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ PathArgs a, double *__restrict__ values)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *codes = smem;
+    const int tid = threadIdx.x;
+    const int64_t local = (int64_t)blockIdx.x * kBlock + tid;
+    if (local >= a.n) return;
+    const int64_t path = a.path0 + local;
+    const int64_t sim = path / a.n_sh;
+    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+    uint32_t cnt[kMaxCat];
+    for (int j = 0; j < kMaxCat; j++) cnt[j] = a.counts[(sim - a.sim0) * kMaxCat + j];
+    gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
+    for (int t = 0; t < a.g.L; t++) {
+        const uint32_t code = (codes[(t >> 3) * kBlock + tid] >> (4 * (t & 7))) & 15u;
+        values[local * a.g.L + t] = a.g.tab[code].v1;
+    }
+}
+
+// ---- exact-order reduction over the paths of one chunk --------------------------------------
+
+// grid (ceil(2^d / 128), 40): partial[arr][j] = raw pairwise sum of node j at depth d
+__global__ void __launch_bounds__(128) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int arr = blockIdx.y;
+    if (j >= ((int64_t)1 << d)) return;
+    int64_t start, len;
+    np_node_at_depth(n, d, j, &start, &len);
+    const double *a = out + (int64_t)arr * ld + start;
+    const double s = np_pairwise_raw(a, len);
+    double mn = a[0], mx = a[0];
+    for (int64_t i = 1; i < len; i++) {
+        const double v = a[i];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    part[(int64_t)arr * pstride + j] = s;
+    part[(int64_t)(40 + arr) * pstride + j] = mn;
+    part[(int64_t)(80 + arr) * pstride + j] = mx;
+}
+
+// one block of 64 threads, thread arr < 40 folds the 2^d partials of its array pairwise
+__global__ void __launch_bounds__(64) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
+{
+    const int arr = threadIdx.x;
+    if (arr >= 40) return;
+    double *p = part + (int64_t)arr * pstride;
+    const int64_t w0 = (int64_t)1 << d;
+    for (int64_t w = w0; w > 1; w >>= 1)
+        for (int64_t i = 0; i < (w >> 1); i++) p[i] = p[2 * i] + p[2 * i + 1];
+    const double *pmn = part + (int64_t)(40 + arr) * pstride, *pmx = part + (int64_t)(80 + arr) * pstride;
+    double mn = pmn[0], mx = pmx[0];
+    for (int64_t i = 1; i < w0; i++) {
+        mn = pmn[i] < mn ? pmn[i] : mn;
+        mx = pmx[i] > mx ? pmx[i] : mx;
+    }
+    if (arr == 0) {
+        rec->first_path = first_path;
+        rec->n_paths = n;
+    }
+    if (arr < 20) {
+        rec->sum_profit[arr] = p[0];
+        rec->min_profit[arr] = mn;
+        rec->max_profit[arr] = mx;
+    } else {
+        rec->sum_dd[arr - 20] = p[0];
+        rec->min_dd[arr - 20] = mn;
+        rec->max_dd[arr - 20] = mx;
+    }
+}
+
+// ---- roofline denominators --------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// 8 independent DADD chains per thread
+__global__ void __launch_bounds__(256) k_peak_dadd(double *out, int iters, double x, unsigned long long *clk)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const long long c0 = clock64();
+    const uint64_t t0 = globaltimer_ns();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = __dadd_rn(a0, x); a1 = __dadd_rn(a1, x); a2 = __dadd_rn(a2, x); a3 = __dadd_rn(a3, x);
+            a4 = __dadd_rn(a4, x); a5 = __dadd_rn(a5, x); a6 = __dadd_rn(a6, x); a7 = __dadd_rn(a7, x);
+        }
+    }
+    const long long c1 = clock64();
+    const uint64_t t1 = globaltimer_ns();
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 1.2345e-300) out[0] = s;
+    if (threadIdx.x == 0) {
+        clk[2 * blockIdx.x] = (unsigned long long)(c1 - c0);
+        clk[2 * blockIdx.x + 1] = (unsigned long long)(t1 - t0);
+    }
+}
+
+// 8 independent integer chains per thread, two ALU instructions (LOP3 + IADD3) per link
+__global__ void __launch_bounds__(256) k_peak_int(unsigned *out, int iters, unsigned x, unsigned y)
+{
+    unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = (a0 ^ x) + y; a1 = (a1 ^ x) + y; a2 = (a2 ^ x) + y; a3 = (a3 ^ x) + y;
+            a4 = (a4 ^ x) + y; a5 = (a5 ^ x) + y; a6 = (a6 ^ x) + y; a7 = (a7 ^ x) + y;
+        }
+    }
+    const unsigned s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (s == 0x12345u) out[0] = s;
+}
+
+}  // namespace mcts

@@ -1,0 +1,667 @@
+// mcts.cu -- host side of libmcts.so: the C ABI of include/mcts.h over the kernels of kernels.cuh.
+// One handle = one device, one stream; every call is chunked over nodes of NumPy's pairwise tree
+// over the path index so that per-chunk partial sums combine to np.mean's exact result.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mcts.h"
+#include "kernels.cuh"
+#include "planner.hpp"
+
+using namespace mcts;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char buf__[512];                                                                             \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return fail(e__ == cudaErrorMemoryAllocation ? MCTS_ENOMEM : MCTS_ECUDA, buf__);            \
+        }                                                                                                \
+    } while (0)
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+struct mcts_handle {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    // device buffers (grow-only)
+    uint32_t *d_counts = nullptr;
+    int64_t cap_sims = 0;
+    double *d_out = nullptr;
+    int64_t cap_paths = 0;
+    double *d_part = nullptr;
+    int64_t cap_part = 0;  // pstride
+    mcts_chunk_result *d_recs = nullptr;
+    int64_t cap_recs = 0;
+    LeafSched *d_sched = nullptr;
+    int64_t sched_L = -1;
+    double *d_values = nullptr;
+    int64_t cap_values = 0;
+    // event pool + timing of the last call
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<EventPair> ev_gen, ev_paths, ev_reduce;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    mcts_timing timing;
+};
+
+static int get_event(mcts_handle *h, cudaEvent_t *e)
+{
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t n;
+        CUDA_TRY(cudaEventCreate(&n));
+        h->ev_pool.push_back(n);
+    }
+    *e = h->ev_pool[h->ev_used++];
+    return MCTS_OK;
+}
+
+static int mark(mcts_handle *h, std::vector<EventPair> &v, bool begin)
+{
+    if (begin) {
+        EventPair p;
+        int rc = get_event(h, &p.a);
+        if (rc) return rc;
+        rc = get_event(h, &p.b);
+        if (rc) return rc;
+        v.push_back(p);
+        CUDA_TRY(cudaEventRecord(p.a, h->stream));
+    } else {
+        CUDA_TRY(cudaEventRecord(v.back().b, h->stream));
+    }
+    return MCTS_OK;
+}
+
+static void timing_reset(mcts_handle *h)
+{
+    h->ev_used = 0;
+    h->ev_gen.clear();
+    h->ev_paths.clear();
+    h->ev_reduce.clear();
+    memset(&h->timing, 0, sizeof h->timing);
+}
+
+static int timing_collect(mcts_handle *h)
+{
+    auto total = [&](std::vector<EventPair> &v, double *ms) -> int {
+        double acc = 0;
+        for (auto &p : v) {
+            float f = 0;
+            CUDA_TRY(cudaEventElapsedTime(&f, p.a, p.b));
+            acc += f;
+        }
+        *ms = acc;
+        return MCTS_OK;
+    };
+    int rc;
+    if ((rc = total(h->ev_gen, &h->timing.gen_ms))) return rc;
+    if ((rc = total(h->ev_paths, &h->timing.paths_ms))) return rc;
+    if ((rc = total(h->ev_reduce, &h->timing.reduce_ms))) return rc;
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, h->ev_begin, h->ev_end));
+    h->timing.total_ms = f;
+    h->timing.paths_launches = (int64_t)h->ev_paths.size();
+    return MCTS_OK;
+}
+
+template <class T>
+static int ensure(T **ptr, int64_t *cap, int64_t need, size_t elem = sizeof(T))
+{
+    if (need <= *cap) return MCTS_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)need * elem);
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "cudaMalloc of %lld bytes failed: %s", (long long)((size_t)need * elem), cudaGetErrorString(e));
+        cudaGetLastError();
+        return fail(MCTS_ENOMEM, buf);
+    }
+    *ptr = (T *)p;
+    *cap = need;
+    return MCTS_OK;
+}
+
+extern "C" {
+
+int mcts_abi_version(void) { return MCTS_ABI_VERSION; }
+
+const char *mcts_last_error(void) { return g_err.c_str(); }
+
+int mcts_create(int device, mcts_handle **out)
+{
+    if (!out) return fail(MCTS_EINVAL, "mcts_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(MCTS_ENODEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libmcts has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(MCTS_ENODEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "device %d (%s) is compute capability %d.%d; libmcts is built for sm_100a only", device, prop.name, prop.major, prop.minor);
+        return fail(MCTS_ENODEVICE, buf);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    mcts_handle *h = new (std::nothrow) mcts_handle();
+    if (!h) return fail(MCTS_ENOMEM, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev_begin));
+    CUDA_TRY(cudaEventCreate(&h->ev_end));
+    CUDA_TRY(cudaMalloc(&h->d_sched, sizeof(LeafSched)));
+    memset(&h->timing, 0, sizeof h->timing);
+    *out = h;
+    return MCTS_OK;
+}
+
+void mcts_destroy(mcts_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_counts);
+    cudaFree(h->d_out);
+    cudaFree(h->d_part);
+    cudaFree(h->d_recs);
+    cudaFree(h->d_sched);
+    cudaFree(h->d_values);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int64_t mcts_sequence_length(const mcts_params *p)
+{
+    if (!p) return fail(MCTS_EINVAL, "params is NULL");
+    GenSpec g;
+    std::string err;
+    mcts_params q = *p;
+    if (q.num_simulations <= 0) q.num_simulations = 1;
+    if (q.num_mc_shuffles <= 0) q.num_mc_shuffles = 1;
+    int rc = build_spec(q, &g, &err);
+    if (rc == MCTS_EEMPTY) return 0;
+    if (rc) return fail(rc, err);
+    return g.L;
+}
+
+int64_t mcts_plan_count(int64_t P, int64_t chunk_paths)
+{
+    if (P <= 0) return 0;
+    std::vector<int64_t> f, c;
+    plan_visit(0, P, clamp_chunk(chunk_paths), &f, &c);
+    return (int64_t)f.size();
+}
+
+int mcts_plan(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_paths)
+{
+    if (P <= 0) return fail(MCTS_EEMPTY, "no paths");
+    std::vector<int64_t> f, c;
+    plan_visit(0, P, clamp_chunk(chunk_paths), &f, &c);
+    for (size_t i = 0; i < f.size(); i++) {
+        first_path[i] = f[i];
+        n_paths[i] = c[i];
+    }
+    return MCTS_OK;
+}
+
+int mcts_combine(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks, mcts_agg *agg)
+{
+    if (P <= 0 || !chunks || !agg) return fail(MCTS_EINVAL, "mcts_combine: bad arguments");
+    const int64_t chunk = clamp_chunk(chunk_paths);
+    std::vector<int64_t> f, c;
+    plan_visit(0, P, chunk, &f, &c);
+    if ((int64_t)f.size() != n_chunks) return fail(MCTS_EINVAL, "mcts_combine: chunk count does not match the plan");
+    std::vector<const mcts_chunk_result *> order(n_chunks);
+    for (int64_t i = 0; i < n_chunks; i++) order[i] = &chunks[i];
+    std::sort(order.begin(), order.end(), [](const mcts_chunk_result *a, const mcts_chunk_result *b) { return a->first_path < b->first_path; });
+    for (int64_t i = 0; i < n_chunks; i++)
+        if (order[i]->first_path != f[i] || order[i]->n_paths != c[i]) return fail(MCTS_EINVAL, "mcts_combine: chunk records do not tile the plan");
+    std::vector<double> part(n_chunks);
+    for (int s = 0; s < MCTS_NSTRAT; s++) {
+        int64_t idx = 0;
+        for (int64_t i = 0; i < n_chunks; i++) part[i] = order[i]->sum_profit[s];
+        agg[s].sum_profit = 0.0 + combine_visit(P, chunk, part.data(), &idx);
+        idx = 0;
+        for (int64_t i = 0; i < n_chunks; i++) part[i] = order[i]->sum_dd[s];
+        agg[s].sum_dd = 0.0 + combine_visit(P, chunk, part.data(), &idx);
+        double mnp = order[0]->min_profit[s], mxp = order[0]->max_profit[s], mnd = order[0]->min_dd[s], mxd = order[0]->max_dd[s];
+        for (int64_t i = 1; i < n_chunks; i++) {
+            mnp = std::min(mnp, order[i]->min_profit[s]);
+            mxp = std::max(mxp, order[i]->max_profit[s]);
+            mnd = std::min(mnd, order[i]->min_dd[s]);
+            mxd = std::max(mxd, order[i]->max_dd[s]);
+        }
+        agg[s].min_profit = mnp;
+        agg[s].max_profit = mxp;
+        agg[s].min_dd = mnd;
+        agg[s].max_dd = mxd;
+        agg[s].count = P;
+    }
+    return MCTS_OK;
+}
+
+int mcts_summary_rows(const mcts_agg *agg, int32_t num_trades, double *rows)
+{
+    if (!agg || !rows) return fail(MCTS_EINVAL, "mcts_summary_rows: NULL argument");
+    for (int s = 0; s < MCTS_NSTRAT; s++) {
+        const double n = (double)agg[s].count;
+        const double avg_p = agg[s].sum_profit / n, avg_d = agg[s].sum_dd / n;  // np.mean = add.reduce / n
+        double *r = rows + 9 * s;
+        r[0] = avg_p;
+        r[1] = avg_d;
+        r[2] = avg_d != 0 ? avg_p / fabs(avg_d) : INFINITY;  // :520
+        r[3] = agg[s].min_profit;
+        r[4] = agg[s].max_profit;
+        r[5] = agg[s].min_dd;
+        r[6] = agg[s].max_dd;
+        r[7] = avg_p / (double)num_trades;                                  // :519
+        r[8] = agg[s].max_dd != 0 ? avg_p / fabs(agg[s].max_dd) : INFINITY;  // :521
+    }
+    return MCTS_OK;
+}
+
+int mcts_get_timing(const mcts_handle *h, mcts_timing *out)
+{
+    if (!h || !out) return fail(MCTS_EINVAL, "mcts_get_timing: NULL argument");
+    *out = h->timing;
+    return MCTS_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+
+static int upload_sched(mcts_handle *h, int64_t L)
+{
+    if (h->sched_L == L) return MCTS_OK;
+    LeafSched s;
+    std::string err;
+    int rc = build_leaf_sched(L, &s, &err);
+    if (rc) return fail(rc, err);
+    CUDA_TRY(cudaMemcpyAsync(h->d_sched, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // `s` is a stack temporary
+    h->timing.h2d_bytes += sizeof s;
+    h->sched_L = L;
+    return MCTS_OK;
+}
+
+static size_t path_smem_bytes(int L) { return (size_t)kTabWords * 4 + (size_t)((L + 7) / 8) * kBlock * 4; }
+
+template <int K, int MODE>
+static int launch_paths_k(mcts_handle *h, const PathArgs &a)
+{
+    const size_t smem = path_smem_bytes(a.g.L);
+    if (smem > 227 * 1024) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~7200 trades)");
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sim_paths<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+    k_sim_paths<K, MODE><<<grid, kBlock, smem, h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->timing.launches++;
+    return MCTS_OK;
+}
+
+template <int MODE>
+static int launch_paths(mcts_handle *h, const PathArgs &a)
+{
+    if (a.g.K <= 2) return launch_paths_k<2, MODE>(h, a);
+    if (a.g.K <= 4) return launch_paths_k<4, MODE>(h, a);
+    return launch_paths_k<8, MODE>(h, a);
+}
+
+static int launch_gen_base(mcts_handle *h, const GenSpec &g, uint64_t seed, int64_t sim0, int64_t n_sims)
+{
+    int rc = ensure(&h->d_counts, &h->cap_sims, n_sims, sizeof(uint32_t) * kMaxCat);
+    if (rc) return rc;
+    if ((rc = mark(h, h->ev_gen, true))) return rc;
+    k_gen_base<<<(unsigned)((n_sims + 127) / 128), 128, 0, h->stream>>>(g, seed, sim0, n_sims, h->d_counts);
+    CUDA_TRY(cudaGetLastError());
+    h->timing.launches++;
+    return mark(h, h->ev_gen, false);
+}
+
+// reduce the [40][ld] per-path rows of one chunk into one record
+static int launch_reduce(mcts_handle *h, int64_t n, int64_t first_path, mcts_chunk_result *d_rec)
+{
+    const int d = reduce_depth(n);
+    const int64_t nodes = (int64_t)1 << d;
+    int rc = ensure(&h->d_part, &h->cap_part, std::max<int64_t>(nodes, 1024) * 120);
+    if (rc) return rc;
+    const int64_t pstride = h->cap_part / 120;
+    if ((rc = mark(h, h->ev_reduce, true))) return rc;
+    dim3 grid((unsigned)((nodes + 127) / 128), 40);
+    k_reduce_nodes<<<grid, 128, 0, h->stream>>>(h->d_out, h->cap_paths, n, d, h->d_part, pstride);
+    CUDA_TRY(cudaGetLastError());
+    k_reduce_top<<<1, 64, 0, h->stream>>>(h->d_part, pstride, d, d_rec, first_path, n);
+    CUDA_TRY(cudaGetLastError());
+    h->timing.launches += 2;
+    return mark(h, h->ev_reduce, false);
+}
+
+static int copy_paths_out(mcts_handle *h, int64_t first, int64_t n, int64_t P, double *profit, double *dd)
+{
+    if (profit) {
+        CUDA_TRY(cudaMemcpy2DAsync(profit + first, (size_t)P * 8, h->d_out, (size_t)h->cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, h->stream));
+        h->timing.d2h_bytes += n * 8 * 20;
+    }
+    if (dd) {
+        CUDA_TRY(cudaMemcpy2DAsync(dd + first, (size_t)P * 8, h->d_out + 20 * h->cap_paths, (size_t)h->cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, h->stream));
+        h->timing.d2h_bytes += n * 8 * 20;
+    }
+    if (profit || dd) CUDA_TRY(cudaStreamSynchronize(h->stream));  // d_out is reused by the next chunk
+    return MCTS_OK;
+}
+
+static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, int64_t cb, int64_t ce,
+                          mcts_chunk_result *out, double *profit, double *dd)
+{
+    if (!h || !p) return fail(MCTS_EINVAL, "NULL handle or params");
+    CUDA_TRY(cudaSetDevice(h->device));
+    GenSpec g;
+    std::string err;
+    int rc = build_spec(*p, &g, &err);
+    if (rc) return fail(rc, err);
+    const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
+    const int64_t chunk = clamp_chunk(opt ? opt->chunk_paths : 0);
+    const int mode = (opt && opt->dedup) ? PM_DEDUP : PM_FULL;
+    std::vector<int64_t> first, count;
+    plan_visit(0, P, chunk, &first, &count);
+    if (cb < 0 || ce > (int64_t)first.size() || cb > ce) return fail(MCTS_EINVAL, "chunk range outside the plan");
+    timing_reset(h);
+    if ((rc = upload_sched(h, g.L))) return rc;
+    int64_t max_n = 0;
+    for (int64_t c = cb; c < ce; c++) max_n = std::max(max_n, count[c]);
+    if (max_n == 0) return MCTS_OK;
+    if (max_n > h->cap_paths) {  // rows must keep 64-byte alignment for the reduction's vector loads
+        if ((rc = ensure(&h->d_out, &h->cap_paths, (max_n + 7) / 8 * 8, sizeof(double) * 40))) return rc;
+    }
+    if ((rc = ensure(&h->d_recs, &h->cap_recs, ce - cb))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    for (int64_t c = cb; c < ce; c++) {
+        const int64_t f = first[c], n = count[c];
+        const int64_t s_lo = f / p->num_mc_shuffles, s_hi = (f + n - 1) / p->num_mc_shuffles;
+        if ((rc = launch_gen_base(h, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
+        PathArgs a;
+        memset(&a, 0, sizeof a);
+        a.g = g;
+        a.seed = seed;
+        a.path0 = f;
+        a.n = n;
+        a.sim0 = s_lo;
+        a.n_sh = p->num_mc_shuffles;
+        a.counts = h->d_counts;
+        a.sched = h->d_sched;
+        a.out = h->d_out;
+        a.ld = h->cap_paths;
+        if ((rc = mark(h, h->ev_paths, true))) return rc;
+        rc = mode == PM_DEDUP ? launch_paths<PM_DEDUP>(h, a) : launch_paths<PM_FULL>(h, a);
+        if (rc) return rc;
+        if ((rc = mark(h, h->ev_paths, false))) return rc;
+        if ((rc = launch_reduce(h, n, f, h->d_recs + (c - cb)))) return rc;
+        if ((rc = copy_paths_out(h, f, n, P, profit, dd))) return rc;
+        h->timing.trade_steps += n * (int64_t)g.L * MCTS_NSTRAT;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_recs, sizeof(mcts_chunk_result) * (size_t)(ce - cb), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * (ce - cb);
+    h->timing.h2d_bytes += (int64_t)sizeof(PathArgs) * (ce - cb);
+    return timing_collect(h);
+}
+
+extern "C" {
+
+int mcts_simulate_chunks(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, int64_t chunk_begin,
+                         int64_t chunk_end, mcts_chunk_result *out)
+{
+    if (!out) return fail(MCTS_EINVAL, "out is NULL");
+    return simulate_range(h, p, seed, opt, chunk_begin, chunk_end, out, nullptr, nullptr);
+}
+
+int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    if (!h || !p || !agg) return fail(MCTS_EINVAL, "NULL argument");
+    const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
+    if (P <= 0) return fail(MCTS_EEMPTY, "zero paths (np.min of an empty list raises in the reference)");
+    const int64_t chunk = opt ? opt->chunk_paths : 0;
+    const int64_t nc = mcts_plan_count(P, chunk);
+    std::vector<mcts_chunk_result> recs((size_t)nc);
+    int rc = simulate_range(h, p, seed, opt, 0, nc, recs.data(), profit, dd);
+    if (rc) return rc;
+    return mcts_combine(P, chunk, recs.data(), nc, agg);
+}
+
+int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    if (!h || !values || !agg) return fail(MCTS_EINVAL, "NULL argument");
+    if (P <= 0 || T <= 0) return fail(MCTS_EEMPTY, "zero paths or an empty trade sequence");
+    if (T > (int64_t)1 << 20) return fail(MCTS_EUNSUPPORTED, "replay sequences longer than 2^20 trades");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int64_t chunk = clamp_chunk(opt ? opt->chunk_paths : 0);
+    chunk = std::max<int64_t>(128, std::min<int64_t>(chunk, ((int64_t)1 << 27) / T));  // <= 1 GiB of values per chunk
+    const int mode = (opt && opt->dedup) ? PM_DEDUP : PM_FULL;
+    std::vector<int64_t> first, count;
+    plan_visit(0, P, chunk, &first, &count);
+    const int64_t nc = (int64_t)first.size();
+    timing_reset(h);
+    int rc;
+    if ((rc = upload_sched(h, T))) return rc;
+    int64_t max_n = *std::max_element(count.begin(), count.end());
+    if (max_n > h->cap_paths && (rc = ensure(&h->d_out, &h->cap_paths, (max_n + 7) / 8 * 8, sizeof(double) * 40))) return rc;
+    if ((rc = ensure(&h->d_values, &h->cap_values, max_n * T))) return rc;
+    if ((rc = ensure(&h->d_recs, &h->cap_recs, nc))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    for (int64_t c = 0; c < nc; c++) {
+        const int64_t f = first[c], n = count[c];
+        CUDA_TRY(cudaMemcpyAsync(h->d_values, values + f * T, (size_t)n * T * 8, cudaMemcpyHostToDevice, h->stream));
+        h->timing.h2d_bytes += n * T * 8;
+        PathArgs a;
+        memset(&a, 0, sizeof a);
+        a.g.L = (int32_t)T;
+        a.path0 = f;
+        a.n = n;
+        a.sched = h->d_sched;
+        a.out = h->d_out;
+        a.ld = h->cap_paths;
+        const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+        if ((rc = mark(h, h->ev_paths, true))) return rc;
+        if (mode == PM_DEDUP) {
+            k_replay_pass<DedupPass0, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            k_replay_pass<DedupPass1, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            k_replay_pass<DedupPass2, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            h->timing.launches += 3;
+        } else {
+            k_replay_pass<FullPass0, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            k_replay_pass<FullPass1, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            k_replay_pass<FullPass2, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            k_replay_pass<FullPass3, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
+            h->timing.launches += 4;
+        }
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = mark(h, h->ev_paths, false))) return rc;
+        if ((rc = launch_reduce(h, n, f, h->d_recs + c))) return rc;
+        if ((rc = copy_paths_out(h, f, n, P, profit, dd))) return rc;
+        h->timing.trade_steps += n * T * MCTS_NSTRAT;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    std::vector<mcts_chunk_result> recs((size_t)nc);
+    CUDA_TRY(cudaMemcpyAsync(recs.data(), h->d_recs, sizeof(mcts_chunk_result) * (size_t)nc, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * nc;
+    if ((rc = timing_collect(h))) return rc;
+    return mcts_combine(P, chunk, recs.data(), nc, agg);
+}
+
+static int path_range_args(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, PathArgs *a)
+{
+    GenSpec g;
+    std::string err;
+    int rc = build_spec(*p, &g, &err);
+    if (rc) return fail(rc, err);
+    const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
+    if (first_path < 0 || n <= 0 || first_path + n > P) return fail(MCTS_EINVAL, "path range outside [0, num_simulations*num_mc_shuffles)");
+    timing_reset(h);
+    if ((rc = upload_sched(h, g.L))) return rc;
+    const int64_t s_lo = first_path / p->num_mc_shuffles, s_hi = (first_path + n - 1) / p->num_mc_shuffles;
+    CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    if ((rc = launch_gen_base(h, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
+    memset(a, 0, sizeof *a);
+    a->g = g;
+    a->seed = seed;
+    a->path0 = first_path;
+    a->n = n;
+    a->sim0 = s_lo;
+    a->n_sh = p->num_mc_shuffles;
+    a->counts = h->d_counts;
+    a->sched = h->d_sched;
+    return MCTS_OK;
+}
+
+int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *values)
+{
+    if (!h || !p || !values) return fail(MCTS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    PathArgs a;
+    int rc = path_range_args(h, p, seed, first_path, n, &a);
+    if (rc) return rc;
+    const int L = a.g.L;
+    if ((rc = ensure(&h->d_values, &h->cap_values, n * L))) return rc;
+    const size_t smem = (size_t)((L + 7) / 8) * kBlock * 4;
+    if (smem > 227 * 1024) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build");
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+#define LAUNCH_SEQ(KK)                                                                                                        \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sequences<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+        k_sequences<KK><<<grid, kBlock, smem, h->stream>>>(a, h->d_values);                                                   \
+    } while (0)
+    if (a.g.K <= 2) LAUNCH_SEQ(2);
+    else if (a.g.K <= 4) LAUNCH_SEQ(4);
+    else LAUNCH_SEQ(8);
+#undef LAUNCH_SEQ
+    CUDA_TRY(cudaGetLastError());
+    h->timing.launches++;
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(values, h->d_values, (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->timing.d2h_bytes += n * L * 8;
+    return timing_collect(h);
+}
+
+int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *curves_dev)
+{
+    if (!h || !p || !curves_dev) return fail(MCTS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    PathArgs a;
+    int rc = path_range_args(h, p, seed, first_path, n, &a);
+    if (rc) return rc;
+    a.curves = curves_dev;
+    a.out = nullptr;
+    if ((rc = mark(h, h->ev_paths, true))) return rc;
+    if ((rc = launch_paths<PM_CURVES>(h, a))) return rc;
+    if ((rc = mark(h, h->ev_paths, false))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->timing.trade_steps = n * (int64_t)a.g.L * MCTS_NSTRAT;
+    return timing_collect(h);
+}
+
+void *mcts_device_alloc(mcts_handle *h, int64_t bytes)
+{
+    if (!h || bytes <= 0) return nullptr;
+    cudaSetDevice(h->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        fail(MCTS_ENOMEM, "cudaMalloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void mcts_device_free(mcts_handle *h, void *ptr)
+{
+    if (!h || !ptr) return;
+    cudaSetDevice(h->device);
+    cudaFree(ptr);
+}
+
+int mcts_copy_to_host(mcts_handle *h, void *dst_host, const void *src_dev, int64_t bytes)
+{
+    if (!h || !dst_host || !src_dev || bytes < 0) return fail(MCTS_EINVAL, "bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MCTS_OK;
+}
+
+int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst_per_s, double *sm_clock_mhz)
+{
+    if (!h) return fail(MCTS_EINVAL, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+    double *d_out = nullptr;
+    unsigned long long *d_clk = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 64));
+    CUDA_TRY(cudaMalloc(&d_clk, sizeof(unsigned long long) * 2 * blocks));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    float ms_d = 0, ms_i = 0;
+    for (int rep = 0; rep < 3; rep++) {  // last repetition counts
+        CUDA_TRY(cudaEventRecord(a, h->stream));
+        k_peak_dadd<<<blocks, threads, 0, h->stream>>>(d_out, iters, 1.0000001, d_clk);
+        CUDA_TRY(cudaEventRecord(b, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventElapsedTime(&ms_d, a, b));
+        CUDA_TRY(cudaEventRecord(a, h->stream));
+        k_peak_int<<<blocks, threads, 0, h->stream>>>((unsigned *)d_out, iters, 0x9e3779b9u, 0x7f4a7c15u);
+        CUDA_TRY(cudaEventRecord(b, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventElapsedTime(&ms_i, a, b));
+    }
+    std::vector<unsigned long long> clk(2 * (size_t)blocks);
+    CUDA_TRY(cudaMemcpy(clk.data(), d_clk, sizeof(unsigned long long) * clk.size(), cudaMemcpyDeviceToHost));
+    std::vector<double> mhz;
+    for (int i = 0; i < blocks; i++)
+        if (clk[2 * i + 1] > 0) mhz.push_back((double)clk[2 * i] / (double)clk[2 * i + 1] * 1e3);
+    std::sort(mhz.begin(), mhz.end());
+    const double ops = (double)blocks * threads * (double)iters * 64.0;
+    if (fp64_inst_per_s) *fp64_inst_per_s = ops / (ms_d * 1e-3);
+    if (int_inst_per_s) *int_inst_per_s = 2.0 * ops / (ms_i * 1e-3);
+    if (sm_clock_mhz) *sm_clock_mhz = mhz.empty() ? 0.0 : mhz[mhz.size() / 2];
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    cudaFree(d_clk);
+    h->timing.launches = 6;
+    return MCTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Monte Carlo path-simulation hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): trade-steps/s = paths x trades x 20 strategies / second.
+Workload: config C5 (scale sweep) -- the "No Markov" three-phase generator of dps_config.yaml
+(hit_rate 0.82, avg_win 186, avg_loss 219), 1000 trades, 20 shuffles per simulation, all 20
+strategy state machines evaluated -- cut into per-step batches of SIMS_PER_GPU_STEP simulations per
+GPU (weak scaling: the full 1e9-path sweep is ~240 such batches per GPU on one GPU).  One step = one
+complete pass of the hot path over one batch: base generation, per-path shuffle, 20 strategies,
+exact-order aggregation (+ the record all_gather and tree combine when N > 1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, NUM_SHUFFLES = 0.82, 186.0, 219.0, 1000, 20
+SIMS_PER_GPU_STEP = 419432          # x 20 shuffles = 8,388,640 paths = 1.68e11 trade-steps per GPU per step
+CHUNK_PATHS = 1 << 21
+METRIC = "trade-steps/sec (paths x trades x strategies)"
+UNIT = "trade-steps/s"
+FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "C5 scale-sweep batch: 'No Markov' 3-phase generator hit_rate=0.82 avg_win=186 avg_loss=219, "
+                    "1000 trades, 20 shuffles/sim, 20 strategies (all 20 state machines evaluated), "
+                    "%d sims (%d paths) per GPU per step" % (SIMS_PER_GPU_STEP, SIMS_PER_GPU_STEP * NUM_SHUFFLES),
+        "paths_per_step": SIMS_PER_GPU_STEP * NUM_SHUFFLES * n_gpus,
+        "trades": NUM_TRADES, "strategies": 20, "generator": "dynamic", "rng": "philox4x32-10, new seed every step",
+        "parallelism": "paths sharded by pairwise-tree node, %d GPU(s), one record all_gather per step" % n_gpus,
+        "l2": "no reusable inputs: every step regenerates its outcomes on device from a new seed; the per-step "
+              "per-path result buffer (40 x 8 B x %d paths per chunk = %d MB) exceeds the 126 MB L2" % (CHUNK_PATHS, 320 * CHUNK_PATHS >> 20),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(target_seconds=12.0, cores=None):
+    """The reference's algorithm on the host cores: oracle/mcts_oracle.c (a C restatement pinned
+    bit-exact to the live Python reference; the Python original is ~100x slower per core and cannot
+    travel to the GPU box).  One independent run_all_strategies per thread."""
+    from oracle import oracle
+    cores = cores or host_cores()
+    prm = oracle.make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, 5, NUM_SHUFFLES)
+    t = oracle.bench(prm, 1, cores)                         # calibration: 100 paths per thread
+    per_sim = max(t / 5, 1e-6)
+    sims = max(5, int(target_seconds / per_sim))
+    prm = oracle.make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, sims, NUM_SHUFFLES)
+    secs = oracle.bench(prm, 1000, cores)
+    steps = cores * sims * NUM_SHUFFLES * NUM_TRADES * 20
+    return {"value": steps / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d threads x %d sims x %d shuffles x %d trades x 20 strategies of the same C5 parameters "
+                      "(oracle/mcts_oracle.c incl. MT19937 + Fisher-Yates), %.1f s wall" % (cores, sims, NUM_SHUFFLES, NUM_TRADES, secs),
+            "seconds": secs, "trade_steps": steps}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU path on the box's host cores (all threads), same
+    metric / config.  Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_step = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_rate(target_seconds=6.0, cores=cores)
+        if i >= args.warmup:
+            per_step.append(base)
+    secs = sum(b["seconds"] for b in per_step)
+    steps = sum(b["trade_steps"] for b in per_step)
+    value = steps / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": per_step[-1]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python (no compilable sources): this arm times oracle/mcts_oracle.c, the C restatement "
+                "pinned bit-exact to it, on all host threads; each step is a bounded sample of the C5 workload",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip dedup / curve-export side measurements")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mc_trade_sizing_b200 import Engine, make_params
+    from mc_trade_sizing_b200 import distributed as mdist
+    from mc_trade_sizing_b200 import trading_models as tm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmcts has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+
+    eng = Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=device)
+    peaks = eng.measure_peaks()
+
+    n_sims = SIMS_PER_GPU_STEP * n_gpus
+    prm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, n_sims, NUM_SHUFFLES)
+    P = n_sims * NUM_SHUFFLES
+    opt = eng.options(chunk_paths=CHUNK_PATHS)
+    steps_per_step_global = P * NUM_TRADES * 20
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stat = {"launches": 0, "paths_ms": 0.0, "paths_launches": 0, "local_trade_steps": 0, "total_ms": 0.0}
+
+    def one_step(seed, record):
+        def compute(lo, hi):
+            recs, n = eng.simulate_chunks(prm, seed, lo, hi, options=opt)
+            if record and hi > lo:
+                t = eng.timing()
+                stat["launches"] += t["launches"]
+                stat["paths_ms"] += t["paths_ms"]
+                stat["paths_launches"] += t["paths_launches"]
+                stat["local_trade_steps"] += t["trade_steps"]
+                stat["total_ms"] += t["total_ms"]
+            return recs, n
+        return mdist.simulate_sharded(prm, seed, compute, rank, world, chunk_paths=CHUNK_PATHS, device=device if world > 1 else None)
+
+    for w in range(args.warmup):
+        one_step(1000 + w, False)
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    last = None
+    for s in range(args.steps):
+        last = one_step(5000 + s, True)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    tmax = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(tmax[0]), float(tmax[1])
+    value = steps_per_step_global * args.steps / (dev_ms * 1e-3)
+
+    # e2e: the public API a user calls (run_all_strategies / its sharded form), host buffers in and out
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        if world == 1:
+            rows = tm.run_all_strategies(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, n_sims, NUM_SHUFFLES, seed=9000 + s,
+                                         device=local_rank, chunk_paths=CHUNK_PATHS)
+        else:
+            rows = mdist.run_all_strategies_sharded(eng, prm, 9000 + s, rank, world, chunk_paths=CHUNK_PATHS, device=device)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t_e2e = (tm.get_engine(local_rank) if world == 1 else eng).timing()
+    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = steps_per_step_global * args.steps / float(e2e_t[0])
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        # (a) the 11 distinct behaviours evaluated once and fanned out (identical results)
+        small = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, SIMS_PER_GPU_STEP // 2, NUM_SHUFFLES)
+        o2 = eng.options(chunk_paths=CHUNK_PATHS, dedup=True)
+        eng.simulate(small, seed=1, options=o2)
+        eng.simulate(small, seed=2, options=o2)
+        t = eng.timing()
+        extras["dedup11_value"] = t["trade_steps"] / (t["total_ms"] * 1e-3)
+        # (b) equity-curve export: HBM-bound, 8 B per trade-step
+        n_curve = 1 << 17
+        eng.export_curves(small, 3, 0, n_curve, to_host=False)
+        eng.export_curves(small, 4, 0, n_curve, to_host=False)
+        t = eng.timing()
+        gbs = t["trade_steps"] * 8 / (t["paths_ms"] * 1e-3) / 1e9
+        extras["curve_export"] = {"trade_steps_per_s": t["trade_steps"] / (t["paths_ms"] * 1e-3), "achieved_gbs": gbs,
+                                  "bytes_per_trade_step": 8, "paths": n_curve}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_file = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks_file = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+    if "curve_export" in extras:
+        extras["curve_export"]["roofline"] = {"bound": "hbm", "achieved": extras["curve_export"]["achieved_gbs"], "peak": hbm_peak,
+                                              "unit": "GB/s", "frac": extras["curve_export"]["achieved_gbs"] / hbm_peak,
+                                              "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback 6.65 TB/s"}
+
+    kernel_rate = stat["local_trade_steps"] / (stat["paths_ms"] * 1e-3)  # this rank's dominant kernel
+    achieved_tflops = FP64_OPS_PER_TRADE_STEP * kernel_rate / 1e12
+    peak_tflops = peaks["fp64_inst_per_s"] / 1e12
+    roofline = {
+        "bound": "fp64-issue", "kernel": "k_sim_paths", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak_tflops, "traffic": None,
+        "definition": "achieved = 6 algorithmic fp64 ops per trade-step (SURVEY 8d) x trade-steps per launch / mean launch "
+                      "duration (CUDA events on the library stream, %d launches); peak = fp64 DADD instruction rate measured "
+                      "in this process by mcts_measure_peaks (MEASURED_PEAKS.json has no fp64 figure), FMA not counted double" % stat["paths_launches"],
+        "kernel_ms_per_launch": stat["paths_ms"] / max(stat["paths_launches"], 1),
+        "kernel_share_of_step": stat["paths_ms"] / max(stat["total_ms"], 1e-9),
+        "int_alu_inst_per_s": peaks["int_inst_per_s"], "fp64_inst_per_s": peaks["fp64_inst_per_s"],
+        "sm_clock_mhz_microbench": peaks["sm_clock_mhz"],
+        "hbm_note": "aggregate mode moves 0.016 B per trade-step (per-path results only); HBM bounds only curve export",
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(n_gpus),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]),
+                "api": "mc_trade_sizing_b200.run_all_strategies (ctypes -> libmcts C ABI, host buffers)" if world == 1 else
+                       "mc_trade_sizing_b200.distributed.run_all_strategies_sharded",
+                "note": "inputs are the scalar arguments of run_all_strategies (kernel parameter blocks), outputs the per-chunk "
+                        "aggregate records; trade outcomes are generated on the device"},
+        "gpu_launches": int(stat["launches"]),
+        "clocks": clocks, "roofline": roofline,
+        "result_check": {"avg_profit_strategy1": float(last[1][0][0]), "expected": 103063.2},
+    }
+    line.update(extras)
+    if not args.no_cpu_baseline and n_gpus == 1:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,8 @@ int mcts_summary_rows(const mcts_agg *agg, int32_t num_trades, double *rows);
 
 /* --- measurement ---------------------------------------------------------------------------- */
 int mcts_get_timing(const mcts_handle *h, mcts_timing *out);
+/* The cudaStream_t every kernel of this handle is launched on (for external CUDA-event timing). */
+void *mcts_get_stream(const mcts_handle *h);
 /* Issue-rate microbenchmarks used as roofline denominators: independent DADD chains
  * and independent IADD3/LOP3 chains over the whole chip. Results in warp-wide... thread-level
  * instructions per second. */

@@ -84,6 +84,7 @@ PROTOTYPES = [
     ("mcts_copy_to_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     ("mcts_summary_rows", C.c_int, [C.POINTER(Agg), C.c_int32, _dp]),
     ("mcts_get_timing", C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    ("mcts_get_stream", C.c_void_p, [C.c_void_p]),
     ("mcts_measure_peaks", C.c_int, [C.c_void_p, _dp, _dp, _dp]),
 ]
 

@@ -295,6 +295,8 @@ int mcts_get_timing(const mcts_handle *h, mcts_timing *out)
     return MCTS_OK;
 }
 
+void *mcts_get_stream(const mcts_handle *h) { return h ? (void *)h->stream : nullptr; }
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

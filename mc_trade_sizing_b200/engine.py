@@ -185,6 +185,10 @@ class Engine:
         _raise(lib().mcts_get_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this engine as an integer (wrap with torch.cuda.ExternalStream for event timing)."""
+        return int(lib().mcts_get_stream(self._h) or 0)
+
     def measure_peaks(self) -> dict:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _raise(lib().mcts_measure_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)))

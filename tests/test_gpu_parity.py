@@ -1,0 +1,279 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of libmcts.so.
+
+  replay   the reference's own post-shuffle sequences (tests/golden/kat.npz, produced by the live
+           reference) -> per-path profit / drawdown of all 20 strategies and the summary rows must be
+           BIT-EXACT (fp64 compared as uint64 patterns)
+  simulate on-device RNG: (a) the per-path results must equal the oracle's evaluation of the very
+           sequences the device generated, bit for bit, (b) aggregates must equal NumPy-ordered
+           aggregation of those per-path values, bit for bit, (c) results must not depend on chunking,
+           (d) distributions must agree with the reference within clustered confidence intervals
+           (tolerance stated in the test)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import harness
+from conftest import assert_bitexact
+from mc_trade_sizing_b200 import Engine, make_params, run_all_strategies
+from mc_trade_sizing_b200 import _ffi
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+README_REGIMES = [
+    {"length": 300, "hit_rate": 0.9, "avg_win": 200, "avg_loss": 100},
+    {"length": 200, "hit_rate": 0.5, "avg_win": 100, "avg_loss": 100},
+    {"length": 500, "hit_rate": 0.2, "avg_win": 100, "avg_loss": 200},
+]
+MODE_KW = {
+    "dynamic": {},
+    "markov1": dict(use_markov=True, p_win_after_win=0.75, p_win_after_loss=0.60),
+    "markov2": dict(use_markov2=True, p_win_ww=0.85, p_win_wl=0.65, p_win_lw=0.55, p_win_ll=0.30),
+    "regime": dict(use_regime=True, regimes=README_REGIMES),
+}
+TIE_GROUPS = [(1, 3), (2, 13), (4, 5, 14, 17), (6, 7), (9, 10, 15), (11, 12)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# replay: bit-exact against the reference
+# ---------------------------------------------------------------------------------------------
+
+def test_replay_golden_sequences_bitexact(eng, kat):
+    for name in sorted(kat["meta"]):
+        meta = kat["meta"][name]
+        seqs = kat[name + "/seqs"]
+        for dedup in (False, True):
+            out = eng.replay(seqs, num_trades=meta["args"][3], options=eng.options(dedup=dedup))
+            assert_bitexact(out["profit"], kat[name + "/profit"], "%s profit dedup=%s" % (name, dedup))
+            assert_bitexact(out["dd"], kat[name + "/dd"], "%s drawdown dedup=%s" % (name, dedup))
+            ids = kat[name + "/rank_ids"]
+            assert_bitexact(out["summary"][ids - 1], kat[name + "/rows"], "%s summary rows" % name)
+
+
+def test_replay_random_values_vs_oracle(eng):
+    rng = np.random.default_rng(3)
+    pool = np.array([204.60000000000002, 167.4, -240.9, 186.0, -219.0, 0.0, -0.0, 1e-3, -7.25])
+    for T in [1, 2, 5, 7, 8, 9, 16, 23, 64, 127, 128, 129, 136, 200, 255, 256, 257, 264, 1000, 1001, 1007, 1100, 2049, 5000]:
+        P = 70 if T < 2000 else 9
+        vals = rng.choice(pool, size=(P, T))
+        vals[0] = rng.normal(size=T) * 100
+        vals[1] = rng.integers(-300, 300, size=T)
+        ref = oracle.eval_paths(vals)
+        out = eng.replay(vals)
+        assert_bitexact(out["profit"], ref["profit"], "T=%d profit" % T)
+        assert_bitexact(out["dd"], ref["dd"], "T=%d dd" % T)
+        assert_bitexact(out["summary"], ref["summary"], "T=%d summary" % T)
+
+
+def test_replay_chunked_aggregates_match_numpy_order(eng):
+    """np.mean over many paths: device chunks are pairwise-tree nodes, so any chunk size is exact."""
+    rng = np.random.default_rng(4)
+    vals = rng.choice([204.60000000000002, 167.4, -240.9, 186.0, -219.0], size=(5000, 64))
+    ref = oracle.eval_paths(vals)
+    for chunk in (128, 1000, 4096, 0):
+        out = eng.replay(vals, options=eng.options(chunk_paths=chunk))
+        assert_bitexact(out["profit"], ref["profit"], "chunk %d profit" % chunk)
+        assert_bitexact(out["summary"], ref["summary"], "chunk %d summary" % chunk)
+        for s in range(20):
+            assert out["summary"][s, 0] == float(np.mean(out["profit"][s])), (chunk, s)
+
+
+def test_replay_int64_regime_arrays(eng, kat):
+    """The reference's regime arrays are int64; fp64 on device is exact for them."""
+    seqs = kat["a5_regime/seqs"]
+    out = eng.replay(seqs.astype(np.int64), num_trades=1000)
+    assert_bitexact(out["profit"], kat["a5_regime/profit"])
+    assert_bitexact(out["dd"], kat["a5_regime/dd"])
+
+
+# ---------------------------------------------------------------------------------------------
+# on-device RNG
+# ---------------------------------------------------------------------------------------------
+
+def _sim_cases():
+    base = (0.82, 186.0, 219.0)
+    cases = []
+    for mode, kw in MODE_KW.items():
+        for T, ns, nsh in ((1000, 40, 20), (37, 9, 5), (8, 5, 3), (5, 4, 3), (1, 3, 2), (129, 7, 4), (1203, 5, 3)):
+            kw2 = dict(kw)
+            if mode == "regime" and T != 1000:
+                kw2["regimes"] = None
+            cases.append(("%s_T%d" % (mode, T), base + (T, ns, nsh), kw2))
+    cases.append(("dps_h0.72", (0.72, 186.0, 219.0, 1000, 30, 20), {}))
+    cases.append(("dps_h0.77", (0.7699999999999999, 186.0, 219.0, 1000, 30, 20), {}))
+    cases.append(("nonint_markov1", (0.6, 186.3, 219.7, 500, 13, 3), MODE_KW["markov1"]))
+    cases.append(("regime_short", base + (1200, 4, 3), MODE_KW["regime"]))
+    cases.append(("regime_trunc", base + (450, 4, 3), MODE_KW["regime"]))
+    return cases
+
+
+def test_simulate_per_path_equals_oracle_on_device_sequences(eng):
+    for name, args, kw in _sim_cases():
+        prm = make_params(*args, **kw)
+        for seed in (12345, 2**63 + 11):
+            seqs = eng.sequences(prm, seed=seed)
+            out = eng.simulate(prm, seed=seed, per_path=True)
+            ref = oracle.eval_paths(seqs, num_trades=args[3])
+            assert_bitexact(out["profit"], ref["profit"], name + " profit")
+            assert_bitexact(out["dd"], ref["dd"], name + " dd")
+            assert_bitexact(out["summary"], ref["summary"], name + " summary")
+            dd = eng.simulate(prm, seed=seed, per_path=True, options=eng.options(dedup=True))
+            assert_bitexact(dd["profit"], out["profit"], name + " dedup profit")
+            assert_bitexact(dd["dd"], out["dd"], name + " dedup dd")
+            assert_bitexact(dd["summary"], out["summary"], name + " dedup summary")
+
+
+def test_device_generator_matches_its_cpu_model(eng):
+    """Sequences from the GPU == the same Philox/urn code run on the host (partition invariance: any
+    path range regenerates identically)."""
+    for name, args, kw in _sim_cases():
+        prm = make_params(*args, **kw)
+        dev = eng.sequences(prm, seed=777)
+        host = harness.simulate(prm, 777, want_eval=False)["seqs"]
+        assert_bitexact(dev, host, name)
+        P = args[4] * args[5]
+        if P > 5:
+            part = eng.sequences(prm, seed=777, first_path=3, n=P - 5)
+            assert_bitexact(part, dev[3:P - 2], name + " sub-range")
+
+
+def test_sequences_are_permutations_of_one_multiset_per_simulation(eng):
+    prm = make_params(0.82, 186.0, 219.0, 1000, 6, 5)
+    seqs = eng.sequences(prm, seed=5)
+    for sim in range(6):
+        block = np.sort(seqs[sim * 5:(sim + 1) * 5], axis=1)
+        assert (block == block[0]).all()
+        assert not (seqs[sim * 5] == seqs[sim * 5 + 1]).all()
+    assert not (np.sort(seqs[0]) == np.sort(seqs[5])).all()
+
+
+def test_simulate_independent_of_chunking(eng):
+    prm = make_params(0.82, 186.0, 219.0, 200, 700, 7)
+    ref = eng.simulate(prm, seed=9, per_path=True)
+    for chunk in (128, 777, 2048):
+        out = eng.simulate(prm, seed=9, per_path=True, options=eng.options(chunk_paths=chunk))
+        assert_bitexact(out["profit"], ref["profit"], "chunk %d" % chunk)
+        assert_bitexact(out["dd"], ref["dd"], "chunk %d" % chunk)
+        assert_bitexact(out["summary"], ref["summary"], "chunk %d" % chunk)
+    assert_bitexact(ref["summary"], oracle.summarise(ref["profit"], ref["dd"], 200), "np.mean order")
+
+
+def test_multi_device_split_combines_exactly(eng):
+    """Emulate G ranks on one GPU: disjoint chunk ranges, host-side tree combine."""
+    prm = make_params(0.82, 186.0, 219.0, 100, 900, 10)
+    P, chunk = 9000, 512
+    ref = eng.simulate(prm, seed=21, options=eng.options(chunk_paths=chunk))
+    first, count = Engine.plan(P, chunk)
+    n = len(first)
+    for G in (2, 3, 8):
+        recs = (_ffi.ChunkResult * n)()
+        bounds = [n * g // G for g in range(G + 1)]
+        for g in reversed(range(G)):  # any order
+            part, m = eng.simulate_chunks(prm, 21, bounds[g], bounds[g + 1], options=eng.options(chunk_paths=chunk))
+            for i in range(m):
+                C.memmove(C.byref(recs[bounds[g] + i]), C.byref(part[i]), C.sizeof(_ffi.ChunkResult))
+        agg = Engine.combine(P, chunk, recs, n)
+        for s in range(20):
+            for f, _ in _ffi.Agg._fields_:
+                a, b = getattr(agg[s], f), getattr(ref["agg"][s], f)
+                assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64), (G, s, f)
+
+
+def _cluster_se(x, n_sh):
+    """standard error of the mean with paths clustered by simulation (shared multiset)."""
+    m = x.reshape(-1, n_sh).mean(axis=1)
+    return m.std(ddof=1) / np.sqrt(m.size)
+
+
+def test_distribution_agrees_with_reference(eng, stats_golden):
+    """Per-strategy mean profit / mean drawdown from the device RNG vs the live reference's sample
+    (tests/golden/stats.npz: 300 sims x 4 shuffles per mode).  Tolerance: |difference| <= 4.5 combined
+    clustered standard errors (two-sided p ~ 7e-6 per comparison, 160 comparisons)."""
+    for mode, kw in MODE_KW.items():
+        meta = stats_golden["meta"][mode]
+        n_sh = meta["args"][5]
+        prm = make_params(0.82, 186.0, 219.0, 1000, 20000, n_sh, **kw)
+        out = eng.simulate(prm, seed=4242, per_path=True)
+        for s in range(20):
+            for key in ("profit", "dd"):
+                ref, dev = stats_golden["%s/%s" % (mode, key)][s], out[key][s]
+                se = np.hypot(_cluster_se(ref, n_sh), _cluster_se(dev, n_sh))
+                assert abs(ref.mean() - dev.mean()) <= 4.5 * se + 1e-9, (mode, s + 1, key, ref.mean(), dev.mean(), se)
+        # spread of the per-path distribution: quantiles within 4.5 bootstrap SE of the reference sample
+        rng = np.random.default_rng(0)
+        for s in (0, 1, 18):
+            ref, dev = stats_golden["%s/profit" % mode][s], out["profit"][s]
+            for q in (0.1, 0.5, 0.9):
+                boots = [np.quantile(rng.choice(ref.reshape(-1, n_sh), size=ref.size // n_sh).ravel(), q) for _ in range(200)]
+                assert abs(np.quantile(ref, q) - np.quantile(dev, q)) <= 4.5 * np.std(boots) + 1e-9, (mode, s + 1, q)
+
+
+def test_analytic_anchor_strategy1(eng):
+    """expected profit of strategy 1 from the chains' exact win-count expectations."""
+    anchors = {"dynamic": 103063.2, "markov1": 66936.7, "markov2": 57802.5, "regime": -19000.0}
+    for mode, kw in MODE_KW.items():
+        prm = make_params(0.82, 186.0, 219.0, 1000, 100000, 1, **kw)
+        out = eng.simulate(prm, seed=1, per_path=True)
+        p = out["profit"][0]
+        se = p.std(ddof=1) / np.sqrt(p.size)
+        assert abs(p.mean() - anchors[mode]) <= 4.5 * se + 0.06, (mode, p.mean(), anchors[mode], se)
+
+
+def test_full_size_markov2_properties(eng):
+    """Config C3 at full size (1e6 paths): size-independent properties."""
+    prm = make_params(0.82, 186.0, 219.0, 1000, 50000, 20, **MODE_KW["markov2"])
+    out = eng.simulate(prm, seed=99, per_path=True)
+    p, d = out["profit"], out["dd"]
+    for g in TIE_GROUPS:
+        for other in g[1:]:
+            assert_bitexact(p[g[0] - 1], p[other - 1], "tie group %s" % (g,))
+            assert_bitexact(d[g[0] - 1], d[other - 1], "tie group %s" % (g,))
+    assert (p[0].reshape(-1, 20) == p[0].reshape(-1, 20)[:, :1]).all()  # strategy 1 is shuffle-invariant (integers)
+    assert (d <= 0).all() and (p == np.round(p)).all()
+    assert (np.abs(p[1]) <= 2 * 219 * 1000).all() and (np.abs(p[17]) <= 3 * 219 * 1000).all()
+    assert_bitexact(out["summary"], oracle.summarise(p, d, 1000), "aggregates in np.mean order")
+    t = eng.timing()
+    assert t["trade_steps"] == 1000000 * 1000 * 20 and t["launches"] > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------------------------
+
+def test_run_all_strategies_drop_in(eng):
+    rows = run_all_strategies(0.82, 186.0, 219.0, 1000, 10, 5, seed=3)
+    assert len(rows) == 20 and all(len(r) == 10 and isinstance(r[0], str) for r in rows)
+    keys = [r[9] for r in rows]
+    pos = [k for k in keys if k >= 0]
+    assert keys[:len(pos)] == sorted(pos, reverse=True)
+    again = run_all_strategies(0.82, 186.0, 219.0, 1000, 10, 5, seed=3)
+    assert rows == again
+    prm = make_params(0.82, 186.0, 219.0, 1000, 10, 5)
+    per = eng.simulate(prm, seed=3, per_path=True)
+    ref = oracle.summarise(per["profit"], per["dd"], 1000)
+    by_desc = {r[0]: r[1:] for r in rows}
+    from mc_trade_sizing_b200.trading_models import DESCRIPTIONS
+    for i in range(20):
+        assert_bitexact(np.array(by_desc[DESCRIPTIONS[i + 1]]), ref[i], "row %d" % (i + 1))
+
+
+def test_error_behaviour(eng):
+    with pytest.raises(ValueError):  # np.min of an empty list raises in the reference
+        eng.simulate(make_params(0.8, 1.0, 1.0, 10, 0, 5))
+    with pytest.raises(ValueError):  # empty sequence
+        eng.simulate(make_params(0.8, 1.0, 1.0, 0, 2, 2))
+    with pytest.raises(ValueError):  # np.random.choice: negative probability
+        eng.simulate(make_params(1.3, 1.0, 1.0, 10, 2, 2))
+    with pytest.raises(ValueError):
+        eng.replay(np.zeros((0, 5)))
+    with pytest.raises(_ffi.MctsError):
+        Engine(99)

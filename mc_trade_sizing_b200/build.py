@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcts.so")
-SOURCES = ["mcts.cu"]
-HEADERS = ["kernels.cuh", "eval_core.cuh", "gen_core.cuh", "pairwise.cuh", "planner.hpp", "spec.hpp",
+SOURCES = ["mcts.cu", "paths_full.cu", "paths_dedup.cu", "paths_curves.cu"]
+HEADERS = ["kernels.cuh", "paths_launch.cuh", "eval_core.cuh", "gen_core.cuh", "pairwise.cuh", "planner.hpp", "spec.hpp",
            os.path.join("..", "..", "include", "mcts.h")]
 
 NVCC_FLAGS = [
@@ -24,8 +24,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-fmad=false",            # equity + value*size must round the product first (no FMA contraction)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+OBJDIR = os.path.join(HERE, "build")
 
 
 def nvcc() -> str:
@@ -43,18 +44,31 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(args):
+    src, obj, extra, verbose = args
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas=-v"] if verbose else []) + ["-c", "-o", obj, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, res.returncode, res.stdout + res.stderr
+
+
 def build_lib(force: bool = False, verbose: bool = False, extra=()) -> str:
+    """Compile every translation unit for sm_100a (in parallel) and link libmcts.so."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
+    jobs = [(os.path.join(CSRC, s), os.path.join(OBJDIR, s.replace(".cu", ".o")), extra, verbose) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(_compile, jobs))
+    for src, rc, log in results:
+        if rc != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
+        if verbose:
+            sys.stderr.write(log)
+    cmd = [nvcc()] + LINK_FLAGS + ["-o", LIB] + [j[1] for j in jobs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -22,8 +22,9 @@
 
 namespace mcts {
 
-constexpr int kBlock = 64;         // threads per block of the path kernels (no intra-block cooperation)
+constexpr int kBlock = 64;         // threads per block of the replay / audit kernels
 constexpr int kBlocksPerSM = 6;    // 384 threads/SM -> up to 168 registers per thread
+constexpr int kThreadsPerSM = 384;
 constexpr int kTabWords = 16 * sizeof(Tab) / 4;
 
 enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
@@ -43,7 +44,7 @@ struct PathArgs {
     double *curves;           // PM_CURVES: [20][ceil(L/2)][n][2]
 };
 
-__global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__ GenSpec g, uint64_t seed, int64_t sim0, int64_t n_sims, uint32_t *__restrict__ counts)
+static __global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__ GenSpec g, uint64_t seed, int64_t sim0, int64_t n_sims, uint32_t *__restrict__ counts)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sims) return;
@@ -111,43 +112,56 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
     });
 }
 
-template <int K, int MODE>
-__global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_sim_paths(const __grid_constant__ PathArgs a)
+// BLOCK threads per block, 384 threads per SM.  The threads of a block do not exchange data; the
+// barriers between phases only keep the warps of a block inside the same ~8 KB loop body so that the
+// instruction caches see few bodies at a time: the kernel is ~100 KB of unrolled code, and with
+// 64-thread blocks and no barriers 47 % of the issue slots were lost to instruction fetch
+// (profiles/r01_ncu_sim_paths_block64_nobarrier.txt).  128 threads (one warp per scheduler, three
+// blocks per SM) measured best; 384 (one block per SM) is 3 % slower.
+template <int K, int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(const __grid_constant__ PathArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     Tab *tab = reinterpret_cast<Tab *>(smem);
     uint32_t *codes = smem + kTabWords;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 16 * 4; i += kBlock) reinterpret_cast<double *>(tab)[i] = reinterpret_cast<const double *>(a.g.tab)[i];
+    for (int i = tid; i < 16 * 4; i += BLOCK) reinterpret_cast<double *>(tab)[i] = reinterpret_cast<const double *>(a.g.tab)[i];
     __syncthreads();
-    const int64_t local = (int64_t)blockIdx.x * kBlock + tid;
-    if (local >= a.n) return;
-    const int64_t path = a.path0 + local;
-    const int64_t sim = path / a.n_sh;
-    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-    uint32_t cnt[kMaxCat];
-    {
+    const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
+    const bool active = local < a.n;
+    if (active) {
+        const int64_t path = a.path0 + local;
+        const int64_t sim = path / a.n_sh;
+        const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+        uint32_t cnt[kMaxCat];
         const uint4 *src = reinterpret_cast<const uint4 *>(a.counts + (sim - a.sim0) * kMaxCat);
         const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
         cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w;
         cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
+        // the code column of a thread is private: the barriers below are for phase alignment only
+        gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
     }
-    // the code column of this thread is private: no barrier between generation and evaluation
-    gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
     CodeSource src;
     src.codes = codes + tid;
-    src.stride = kBlock;
+    src.stride = BLOCK;
     src.tab = tab;
     src.word = 0;
     if constexpr (MODE == PM_DEDUP) {
-        run_pass<DedupPass0, MODE>(src, a, local);
-        run_pass<DedupPass1, MODE>(src, a, local);
-        run_pass<DedupPass2, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<DedupPass0, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<DedupPass1, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<DedupPass2, MODE>(src, a, local);
     } else {
-        run_pass<FullPass0, MODE>(src, a, local);
-        run_pass<FullPass1, MODE>(src, a, local);
-        run_pass<FullPass2, MODE>(src, a, local);
-        run_pass<FullPass3, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<FullPass0, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<FullPass1, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<FullPass2, MODE>(src, a, local);
+        __syncthreads();
+        if (active) run_pass<FullPass3, MODE>(src, a, local);
     }
 }
 
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ Pa
 // ---- exact-order reduction over the paths of one chunk --------------------------------------
 
 // grid (ceil(2^d / 128), 40): partial[arr][j] = raw pairwise sum of node j at depth d
-__global__ void __launch_bounds__(128) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
+static __global__ void __launch_bounds__(128) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int arr = blockIdx.y;
@@ -206,7 +220,7 @@ __global__ void __launch_bounds__(128) k_reduce_nodes(const double *__restrict__
 }
 
 // one block of 64 threads, thread arr < 40 folds the 2^d partials of its array pairwise
-__global__ void __launch_bounds__(64) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
+static __global__ void __launch_bounds__(64) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
 {
     const int arr = threadIdx.x;
     if (arr >= 40) return;
@@ -245,7 +259,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns()
 }
 
 // 8 independent DADD chains per thread
-__global__ void __launch_bounds__(256) k_peak_dadd(double *out, int iters, double x, unsigned long long *clk)
+static __global__ void __launch_bounds__(256) k_peak_dadd(double *out, int iters, double x, unsigned long long *clk)
 {
     double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const long long c0 = clock64();
@@ -268,7 +282,7 @@ __global__ void __launch_bounds__(256) k_peak_dadd(double *out, int iters, doubl
 }
 
 // 8 independent integer chains per thread, two ALU instructions (LOP3 + IADD3) per link
-__global__ void __launch_bounds__(256) k_peak_int(unsigned *out, int iters, unsigned x, unsigned y)
+static __global__ void __launch_bounds__(256) k_peak_int(unsigned *out, int iters, unsigned x, unsigned y)
 {
     unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     for (int it = 0; it < iters; it++) {

@@ -41,6 +41,7 @@ struct EventPair {
 struct mcts_handle {
     int device = 0;
     int sm_count = 0;
+    int block_threads = 0;  // experiment override (mcts_options.block_threads)
     cudaStream_t stream = nullptr;
     // device buffers (grow-only)
     uint32_t *d_counts = nullptr;
@@ -315,27 +316,48 @@ static int upload_sched(mcts_handle *h, int64_t L)
     return MCTS_OK;
 }
 
-static size_t path_smem_bytes(int L) { return (size_t)kTabWords * 4 + (size_t)((L + 7) / 8) * kBlock * 4; }
+static size_t path_smem_bytes(int L, int block) { return (size_t)kTabWords * 4 + (size_t)((L + 7) / 8) * block * 4; }
 
-template <int K, int MODE>
-static int launch_paths_k(mcts_handle *h, const PathArgs &a)
+// defined in paths_<mode>.cu (one translation unit per PathMode so they compile in parallel)
+cudaError_t mcts_launch_paths_full(const PathArgs &a, int block, cudaStream_t stream);
+cudaError_t mcts_launch_paths_dedup(const PathArgs &a, int block, cudaStream_t stream);
+cudaError_t mcts_launch_paths_curves(const PathArgs &a, int block, cudaStream_t stream);
+
+// Block size: the largest of 128 / 64 / 32 that keeps at least 80 % of the best achievable number
+// of threads resident per SM given the shared-memory code columns (4 bits per trade per thread,
+// 227 KB per SM, 1 KB reserved per block).  Larger blocks are preferred because their warps stay in
+// the same unrolled loop body (instruction-cache locality, see k_sim_paths).  `want`
+// (mcts_options.block_threads) overrides for experiments.
+static int pick_block(int L, int want)
 {
-    const size_t smem = path_smem_bytes(a.g.L);
-    if (smem > 227 * 1024) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~7200 trades)");
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sim_paths<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
-    k_sim_paths<K, MODE><<<grid, kBlock, smem, h->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    h->timing.launches++;
-    return MCTS_OK;
+    const int cands[3] = {128, 64, 32};
+    int resident[3] = {0, 0, 0}, best = 0;
+    for (int i = 0; i < 3; i++) {
+        const size_t smem = path_smem_bytes(L, cands[i]);
+        if (smem > 227 * 1024) continue;
+        if (want == cands[i]) return want;
+        const int by_smem = (int)((size_t)228 * 1024 / (smem + 1024));
+        resident[i] = std::min(kThreadsPerSM / cands[i], by_smem) * cands[i];
+        best = std::max(best, resident[i]);
+    }
+    for (int i = 0; i < 3; i++)
+        if (resident[i] > 0 && resident[i] * 5 >= best * 4) return cands[i];
+    return 0;
 }
 
-template <int MODE>
-static int launch_paths(mcts_handle *h, const PathArgs &a)
+static int launch_paths(mcts_handle *h, int mode, const PathArgs &a)
 {
-    if (a.g.K <= 2) return launch_paths_k<2, MODE>(h, a);
-    if (a.g.K <= 4) return launch_paths_k<4, MODE>(h, a);
-    return launch_paths_k<8, MODE>(h, a);
+    const int block = pick_block(a.g.L, h->block_threads);
+    if (!block) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~14000 trades)");
+    cudaError_t e;
+    switch (mode) {
+        case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, h->stream); break;
+        case PM_CURVES: e = mcts_launch_paths_curves(a, block, h->stream); break;
+        default: e = mcts_launch_paths_full(a, block, h->stream); break;
+    }
+    if (e != cudaSuccess) return fail(MCTS_ECUDA, std::string("k_sim_paths launch failed: ") + cudaGetErrorString(e));
+    h->timing.launches++;
+    return MCTS_OK;
 }
 
 static int launch_gen_base(mcts_handle *h, const GenSpec &g, uint64_t seed, int64_t sim0, int64_t n_sims)
@@ -393,6 +415,7 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
     const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
     const int64_t chunk = clamp_chunk(opt ? opt->chunk_paths : 0);
     const int mode = (opt && opt->dedup) ? PM_DEDUP : PM_FULL;
+    h->block_threads = opt ? opt->block_threads : 0;
     std::vector<int64_t> first, count;
     plan_visit(0, P, chunk, &first, &count);
     if (cb < 0 || ce > (int64_t)first.size() || cb > ce) return fail(MCTS_EINVAL, "chunk range outside the plan");
@@ -423,7 +446,7 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
         a.out = h->d_out;
         a.ld = h->cap_paths;
         if ((rc = mark(h, h->ev_paths, true))) return rc;
-        rc = mode == PM_DEDUP ? launch_paths<PM_DEDUP>(h, a) : launch_paths<PM_FULL>(h, a);
+        rc = launch_paths(h, mode, a);
         if (rc) return rc;
         if ((rc = mark(h, h->ev_paths, false))) return rc;
         if ((rc = launch_reduce(h, n, f, h->d_recs + (c - cb)))) return rc;
@@ -586,7 +609,7 @@ int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int6
     a.curves = curves_dev;
     a.out = nullptr;
     if ((rc = mark(h, h->ev_paths, true))) return rc;
-    if ((rc = launch_paths<PM_CURVES>(h, a))) return rc;
+    if ((rc = launch_paths(h, PM_CURVES, a))) return rc;
     if ((rc = mark(h, h->ev_paths, false))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));

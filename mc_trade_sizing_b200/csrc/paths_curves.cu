@@ -1,0 +1,2 @@
+#include "paths_launch.cuh"
+MCTS_DEFINE_PATH_LAUNCHER(mcts_launch_paths_curves, mcts::PM_CURVES)

@@ -1,0 +1,44 @@
+// paths_launch.cuh -- explicit instantiations of k_sim_paths for ONE PathMode; included by the
+// paths_*.cu translation units so that the big unrolled kernels compile in parallel.
+#pragma once
+#include "kernels.cuh"
+
+namespace mcts {
+
+inline size_t path_smem_bytes(int L, int block) { return (size_t)kTabWords * 4 + (size_t)((L + 7) / 8) * block * 4; }
+
+template <int K, int MODE, int BLOCK>
+static cudaError_t launch_kb(const PathArgs &a, cudaStream_t stream)
+{
+    const size_t smem = path_smem_bytes(a.g.L, BLOCK);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_sim_paths<K, MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned grid = (unsigned)((a.n + BLOCK - 1) / BLOCK);
+    k_sim_paths<K, MODE, BLOCK><<<grid, BLOCK, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K, int MODE>
+static cudaError_t launch_k(const PathArgs &a, int block, cudaStream_t stream)
+{
+    switch (block) {
+        case 128: return launch_kb<K, MODE, 128>(a, stream);
+        case 64: return launch_kb<K, MODE, 64>(a, stream);
+        case 32: return launch_kb<K, MODE, 32>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const PathArgs &a, int block, cudaStream_t stream)
+{
+    if (a.g.K <= 2) return launch_k<2, MODE>(a, block, stream);
+    return launch_k<8, MODE>(a, block, stream);
+}
+
+}  // namespace mcts
+
+#define MCTS_DEFINE_PATH_LAUNCHER(NAME, MODE) \
+    cudaError_t NAME(const mcts::PathArgs &a, int block, cudaStream_t stream) { return mcts::launch_mode<MODE>(a, block, stream); }

@@ -159,5 +159,52 @@ def main():
     print("numpy", np.__version__, "python", sys.version.split()[0])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--cli" not in sys.argv:
     main()
+
+
+def make_cli_golden():
+    """stdout of the reference's own main() (src/trading_models.py:532-671) with run_all_strategies
+    replaced by a stub that returns the rows captured in kat.npz -- pins the CLI text format
+    (settings block, break-even line, table, rule after row 3) independently of the RNG."""
+    import contextlib
+    import io
+    tm = load_reference()
+    desc = descriptions_by_id(tm)
+    kat = np.load(os.path.join(HERE, "kat.npz"))
+    cases = {
+        "a5_dynamic": ["--hit_rate", "0.82", "--avg_win", "186.0", "--avg_loss", "219.0", "--num_simulations", "3",
+                       "--num_trades", "1000", "--num_mc_shuffles", "2"],
+        "a5_markov1": ["--hit_rate", "0.7699999999999999", "--avg_win", "186.0", "--avg_loss", "219.0", "--num_simulations", "3",
+                       "--num_trades", "1000", "--num_mc_shuffles", "2", "--use_markov", "--p_win_after_win", "0.75",
+                       "--p_win_after_loss", "0.6"],
+        "a5_markov2": ["--hit_rate", "0.72", "--avg_win", "186.0", "--avg_loss", "219.0", "--num_simulations", "3",
+                       "--num_trades", "1000", "--num_mc_shuffles", "2", "--use_markov2", "--p_win_ww", "0.85", "--p_win_wl", "0.65",
+                       "--p_win_lw", "0.55", "--p_win_ll", "0.3"],
+        "a5_regime": ["--hit_rate", "0.82", "--avg_win", "186.0", "--avg_loss", "219.0", "--num_simulations", "3",
+                      "--num_trades", "1000", "--num_mc_shuffles", "2", "--use_regime", "--regimes", json.dumps(README_REGIMES)],
+    }
+    out = {}
+    sys.modules["colorama"] = None  # the reference prints the plain variant when colorama is absent (:647-671)
+    for name, argv in cases.items():
+        ids, rows = kat[name + "/rank_ids"], kat[name + "/rows"]
+        table = [(desc[int(i)],) + tuple(np.float64(x) for x in r) for i, r in zip(ids, rows)]
+        orig = tm.run_all_strategies
+        tm.run_all_strategies = lambda *a, **k: table
+        buf = io.StringIO()
+        old_argv = sys.argv
+        sys.argv = ["trading_models.py"] + argv
+        try:
+            with contextlib.redirect_stdout(buf):
+                tm.main()
+        finally:
+            sys.argv = old_argv
+            tm.run_all_strategies = orig
+        out[name] = {"argv": argv, "stdout": buf.getvalue()}
+        print("cli", name, len(buf.getvalue()), "bytes")
+    with open(os.path.join(HERE, "cli.json"), "w") as f:
+        json.dump(out, f, indent=1, ensure_ascii=False)
+
+
+if __name__ == "__main__" and "--cli" in sys.argv:
+    make_cli_golden()

@@ -1,0 +1,93 @@
+"""CPU unit tests of the DEVICE generator code (csrc/gen_core.cuh via tests/cpu_harness): Philox
+known answers, base-sequence laws, urn shuffle, counter keying."""
+import numpy as np
+
+import harness
+from conftest import assert_bitexact
+from mc_trade_sizing_b200 import make_params
+from oracle import oracle
+
+README_REGIMES = [
+    {"length": 300, "hit_rate": 0.9, "avg_win": 200, "avg_loss": 100},
+    {"length": 200, "hit_rate": 0.5, "avg_win": 100, "avg_loss": 100},
+    {"length": 500, "hit_rate": 0.2, "avg_win": 100, "avg_loss": 200},
+]
+MODE_KW = {
+    "dynamic": {},
+    "markov1": dict(use_markov=True, p_win_after_win=0.75, p_win_after_loss=0.60),
+    "markov2": dict(use_markov2=True, p_win_ww=0.85, p_win_wl=0.65, p_win_lw=0.55, p_win_ll=0.30),
+    "regime": dict(use_regime=True, regimes=README_REGIMES),
+}
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors (kat_vectors: philox4x32 10)."""
+    assert harness.philox((0, 0), (0, 0, 0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert harness.philox((0xffffffff, 0xffffffff), (0xffffffff,) * 4) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert harness.philox((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_sequence_lengths_match_reference_generators(kat):
+    """L is what the reference generators return (Markov-2 >= 2 trades, short / truncated regimes...)."""
+    for name, meta in kat["meta"].items():
+        prm = make_params(*meta["args"], **meta["kwargs"])
+        _, _, L = harness.base_counts(prm, 1, 0)
+        assert L == kat[name + "/seqs"].shape[1], name
+
+
+def test_base_counts_follow_the_generator_laws():
+    """Mean win counts per category over many simulations vs the chains' exact expectations."""
+    n = 4000
+    prm = make_params(0.82, 186.0, 219.0, 1000, n, 1)
+    acc = np.zeros(8)
+    for sim in range(n):
+        c, vals, L = harness.base_counts(prm, 99, sim)
+        assert c.sum() == 1000 and L == 1000
+        acc[:len(c)] += c
+    by_val = dict(zip(vals, acc[:len(vals)] / n))
+    assert by_val[204.60000000000002] == 200 and by_val[-197.1] == 0          # p = min(0.82+0.2, 1) = 1
+    assert abs(by_val[167.4] - 200 * 0.52) < 4 * np.sqrt(200 * 0.52 * 0.48 / n)
+    assert abs(by_val[186.0] - 600 * 0.82) < 4 * np.sqrt(600 * 0.82 * 0.18 / n)
+    # Markov-1 stationary-ish win fraction: p = 0.6 / (1 - 0.75 + 0.6)
+    prm = make_params(0.82, 186.0, 219.0, 1000, n, 1, **MODE_KW["markov1"])
+    wins = np.array([harness.base_counts(prm, 5, s)[0][0] for s in range(1500)])
+    assert abs(wins.mean() / 1000 - 0.6 / 0.85) < 0.003
+
+
+def test_paths_are_uniform_permutations_of_the_simulation_multiset():
+    prm = make_params(0.82, 186.0, 219.0, 64, 3, 400)
+    seqs = harness.simulate(prm, 7, want_eval=False)["seqs"]
+    for sim in range(3):
+        block = seqs[sim * 400:(sim + 1) * 400]
+        srt = np.sort(block, axis=1)
+        assert (srt == srt[0]).all()
+        # every position sees every value with the multiset's frequency (uniformity, 5 sigma)
+        for v in np.unique(block[0]):
+            frac = (block[0] == v).mean()
+            per_pos = (block == v).mean(axis=0)
+            assert np.all(np.abs(per_pos - frac) < 5 * np.sqrt(frac * (1 - frac) / 400) + 1e-12)
+
+
+def test_counter_keying_is_partition_invariant():
+    prm = make_params(0.82, 186.0, 219.0, 203, 9, 7, **MODE_KW["regime"] | {"regimes": None})
+    full = harness.simulate(prm, 123456789012345)
+    part = harness.simulate(prm, 123456789012345, first_path=17, n=30)
+    assert_bitexact(part["seqs"], full["seqs"][17:47])
+    assert_bitexact(part["profit"], full["profit"][:, 17:47])
+    other = harness.simulate(prm, 123456789012346, first_path=17, n=30)
+    assert not (other["seqs"] == part["seqs"]).all()
+
+
+def test_simulated_paths_evaluate_like_the_reference():
+    """device-generated sequences + device evaluator (categorical code path) == oracle on the same sequences"""
+    for mode, kw in MODE_KW.items():
+        for T in (1000, 129, 37, 8, 5, 1):
+            kw2 = dict(kw)
+            if mode == "regime" and T != 1000:
+                kw2["regimes"] = None
+            prm = make_params(0.82, 186.0, 219.0, T, 5, 4, **kw2)
+            out = harness.simulate(prm, 12345)
+            ref = oracle.eval_paths(out["seqs"])
+            assert_bitexact(out["profit"], ref["profit"], "%s T=%d profit" % (mode, T))
+            assert_bitexact(out["dd"], ref["dd"], "%s T=%d dd" % (mode, T))

@@ -93,11 +93,12 @@ struct History {
     uint32_t w, l;  // win / loss bits of the previous block (nibble LSBs)
 };
 
+// Mask bits sit at position 4*i + 1 (never bit 0: a test of bit 0 costs ptxas an extra compare).
 MCTS_HD Masks make_masks(uint32_t W, uint32_t Lb, History &h)
 {
     Masks m;
-    const uint32_t pw = (W << 4) | (h.w >> 28), ppw = (W << 8) | (h.w >> 24);
-    const uint32_t pl = (Lb << 4) | (h.l >> 28), ppl = (Lb << 8) | (h.l >> 24);
+    const uint32_t pw = (W << 5) | (h.w >> 27), ppw = (W << 9) | (h.w >> 23);
+    const uint32_t pl = (Lb << 5) | (h.l >> 27), ppl = (Lb << 9) | (h.l >> 23);
     m.pw = pw;
     m.pl = pl;
     m.pww = pw & ppw;
@@ -108,21 +109,34 @@ MCTS_HD Masks make_masks(uint32_t W, uint32_t Lb, History &h)
     h.l = Lb;
     return m;
 }
+MCTS_HD constexpr uint32_t mask_bit(int i) { return 2u << (4 * i); }
+
+// p ? v2 : v1 where v2 == 2*v1.  SHARED_LO: the caller guarantees that v1 is zero or a normal number
+// whose double is finite (checked on the host for the categorical path), so v2 and v1 have the same
+// low word and only the high word needs a select -- one ALU instruction instead of two.
+template <bool SHARED_LO>
+MCTS_HD double select_double_or_single(bool p, double v2, double v1)
+{
+#if defined(__CUDA_ARCH__)
+    if constexpr (SHARED_LO) return __hiloint2double(p ? __double2hiint(v2) : __double2hiint(v1), __double2loint(v1));
+#endif
+    return p ? v2 : v1;
+}
 
 // contribution of the current trade for one behaviour: a select among {0, v, 2v, fl(3v)}
-template <int RULE>
+template <int RULE, bool SHARED_LO>
 MCTS_HD double contribution(const Masks &m, uint32_t bit, double v1, double v2, double v3)
 {
     if constexpr (RULE == R_C1) return v1;
-    if constexpr (RULE == R_AM) return (m.pw & bit) ? v2 : v1;
-    if constexpr (RULE == R_F1) return (m.fw & bit) ? v2 : v1;
-    if constexpr (RULE == R_MG) return (m.pl & bit) ? v2 : v1;
-    if constexpr (RULE == R_MG2) return (m.pll & bit) ? v2 : v1;
+    if constexpr (RULE == R_AM) return select_double_or_single<SHARED_LO>((m.pw & bit) != 0, v2, v1);
+    if constexpr (RULE == R_F1) return select_double_or_single<SHARED_LO>((m.fw & bit) != 0, v2, v1);
+    if constexpr (RULE == R_MG) return select_double_or_single<SHARED_LO>((m.pl & bit) != 0, v2, v1);
+    if constexpr (RULE == R_MG2) return select_double_or_single<SHARED_LO>((m.pll & bit) != 0, v2, v1);
     if constexpr (RULE == R_P1) return (m.pw & bit) ? 0.0 : v1;
     if constexpr (RULE == R_P2) return (m.pww & bit) ? 0.0 : v1;
-    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0.0 : ((m.s16 & bit) ? v2 : v1);
+    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0.0 : select_double_or_single<SHARED_LO>((m.s16 & bit) != 0, v2, v1);
     if constexpr (RULE == R_S18) return (m.pww & bit) ? v3 : v1;
-    if constexpr (RULE == R_S19) return (m.pww & bit) ? v2 : ((m.pll & bit) ? v3 : v1);
+    if constexpr (RULE == R_S19) return (m.pll & bit) ? v3 : select_double_or_single<SHARED_LO>((m.pww & bit) != 0, v2, v1);
     if constexpr (RULE == R_S20) return (m.pll & bit) ? v3 : v1;
     return v1;
 }
@@ -191,11 +205,11 @@ MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t
         constexpr int i = decltype(I)::value;
         double v1, v2, v3;
         src.template get<i>(v1, v2, v3);
-        constexpr uint32_t bit = 1u << (4 * i);
+        constexpr uint32_t bit = mask_bit(i);
         static_for<IDS::N>([&](auto S) {
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
-            const double c = contribution<rule>(m, bit, v1, v2, v3);
+            const double c = contribution<rule, SRC::kSharedLo>(m, bit, v1, v2, v3);
             trade_step(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
@@ -211,11 +225,11 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
     for (int i = 0; i < count; i++) {
         double v1, v2, v3;
         src.get_dyn(i, v1, v2, v3);
-        const uint32_t bit = 1u << (4 * i);
+        const uint32_t bit = mask_bit(i);
         static_for<IDS::N>([&](auto S) {
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
-            const double c = contribution<rule>(m, bit, v1, v2, v3);
+            const double c = contribution<rule, SRC::kSharedLo>(m, bit, v1, v2, v3);
             trade_step(a.E[s], a.peak[s], a.dd[s], res[s], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
@@ -277,6 +291,7 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
 
 // categorical: 8 trades per 32-bit word, 4-bit code each; code -> {v, 2v, fl(3v)} table
 struct CodeSource {
+    static constexpr bool kSharedLo = true;  // build_spec rejects subnormal / overflowing values
     const uint32_t *codes;  // word of block `oct` at codes[oct * stride]
     int stride;
     const Tab *tab;
@@ -322,6 +337,7 @@ MCTS_HD double mul_rn(double a, double b)
 
 // replay: arbitrary fp64 trade results of one path, contiguous in memory
 struct ValueSource {
+    static constexpr bool kSharedLo = false;  // arbitrary caller values
     const double *row;
     double v[8];
     MCTS_HD uint32_t load(int oct)

@@ -191,4 +191,64 @@ MCTS_HD void gen_path_codes(const GenSpec &g, uint64_t seed, uint32_t sim, uint3
     }
 }
 
+// Fisher-Yates over the packed codes (any number of categories).  The code column is first filled in
+// base order (runs of each category, in category order), then shuffled from the top exactly like
+// RandomState.shuffle (:492):  for i = L-1 .. 1:  j = mulhi32(x_i, i + 1);  swap(a_i, a_j),
+// x_i = word (i%4) of Philox(ctr = (i/4, k, sim, 1)).  The word holding position i lives in a register
+// while i sweeps through it; a_j is read-modify-written in (thread-private) shared memory.
+MCTS_HD void gen_path_codes_fy(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t k, const uint32_t *counts, uint32_t *codes, int stride)
+{
+    const uint32_t L = (uint32_t)g.L;
+    const int n_words = (int)((L + 7u) >> 3);
+    const uint32_t rank_codes_lo = g.rank_codes, rank_codes_hi = g.rank_codes_hi;
+    {
+        int cat = 0;
+        uint32_t end = counts[0];
+        uint32_t code = rank_codes_lo & 15u;
+        for (int w = 0; w < n_words; w++) {
+            const uint32_t t0 = 8u * (uint32_t)w;
+            uint32_t word;
+            if (t0 + 8u <= end) {
+                word = code * 0x11111111u;
+            } else {
+                word = 0;
+                for (uint32_t i = 0; i < 8u; i++) {
+                    const uint32_t t = t0 + i;
+                    while (t >= end && cat < g.K - 1) {
+                        cat++;
+                        end += counts[cat];
+                        code = ((cat < 8 ? rank_codes_lo >> (4 * cat) : rank_codes_hi >> (4 * (cat - 8)))) & 15u;
+                    }
+                    if (t < L) word |= code << (4u * i);
+                }
+            }
+            codes[(size_t)w * stride] = word;
+        }
+    }
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int w = n_words - 1; w >= 0; w--) {
+        uint32_t cur = codes[(size_t)w * stride];
+        uint32_t xa[4], xb[4];
+        philox4x32_10(k0, k1, 2u * w, k, sim, kStreamShuffle, xa);
+        philox4x32_10(k0, k1, 2u * w + 1u, k, sim, kStreamShuffle, xb);
+        const bool full = 8u * (uint32_t)w + 8u <= L;
+#pragma unroll
+        for (int p = 7; p >= 0; p--) {
+            const uint32_t i = 8u * (uint32_t)w + (uint32_t)p;
+            if (full || i < L) {
+                const uint32_t j = mulhi32(p < 4 ? xa[p] : xb[p - 4], i + 1u);
+                const uint32_t wj = j >> 3, sh = (j & 7u) << 2;
+                const uint32_t tj = codes[(size_t)wj * stride];
+                const bool alias = wj == (uint32_t)w;  // then the live copy is `cur`, the stored one is stale
+                const uint32_t srcw = alias ? cur : tj;
+                const uint32_t d = ((srcw >> sh) ^ (cur >> (4 * p))) & 15u;  // a_i ^ a_j
+                const uint32_t dsh = d << sh;
+                cur = cur ^ (d << (4 * p)) ^ (alias ? dsh : 0u);
+                codes[(size_t)wj * stride] = tj ^ dsh;  // for an aliased word this is overwritten below
+            }
+        }
+        codes[(size_t)w * stride] = cur;
+    }
+}
+
 }  // namespace mcts

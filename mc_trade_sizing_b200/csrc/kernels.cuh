@@ -3,7 +3,7 @@
 //   k_gen_base      one thread per simulation: category counts of the base sequence (generators
 //                   src/trading_models.py:43-128 on Philox uniforms)
 //   k_sim_paths     THE hot kernel, one thread per path (= simulation x shuffle, :491-507):
-//                   urn-draw the shuffled outcome sequence into a thread-private shared-memory
+//                   shuffle the simulation's outcome multiset (Fisher-Yates; urn for 2 values) into a thread-private shared-memory
 //                   column (4 bits per trade), then evaluate the 20 strategies in passes of five with
 //                   equity/peak/drawdown/profit accumulators in fp64 registers; per-path results
 //                   go to HBM once (320 B per path = 0.016 B per trade-step)
@@ -51,8 +51,8 @@ static __global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__
     uint32_t c[kMaxCat];
     gen_base_counts(g, seed, (uint32_t)(sim0 + i), c);
     uint4 *dst = reinterpret_cast<uint4 *>(counts + i * kMaxCat);
-    dst[0] = make_uint4(c[0], c[1], c[2], c[3]);
-    dst[1] = make_uint4(c[4], c[5], c[6], c[7]);
+#pragma unroll
+    for (int q = 0; q < kMaxCat / 4; q++) dst[q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
 }
 
 // equity-curve sink: two consecutive trades per 128-bit store, paths contiguous
@@ -133,13 +133,14 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
         const int64_t path = a.path0 + local;
         const int64_t sim = path / a.n_sh;
         const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-        uint32_t cnt[kMaxCat];
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.counts + (sim - a.sim0) * kMaxCat);
-        const uint4 c0 = __ldg(src), c1 = __ldg(src + 1);
-        cnt[0] = c0.x; cnt[1] = c0.y; cnt[2] = c0.z; cnt[3] = c0.w;
-        cnt[4] = c1.x; cnt[5] = c1.y; cnt[6] = c1.z; cnt[7] = c1.w;
+        const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
         // the code column of a thread is private: the barriers below are for phase alignment only
-        gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
+        if constexpr (K == 2) {
+            const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
+            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, BLOCK);
+        } else {
+            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
+        }
     }
     CodeSource src;
     src.codes = codes + tid;
@@ -187,9 +188,13 @@ __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ Pa
     const int64_t path = a.path0 + local;
     const int64_t sim = path / a.n_sh;
     const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-    uint32_t cnt[kMaxCat];
-    for (int j = 0; j < kMaxCat; j++) cnt[j] = a.counts[(sim - a.sim0) * kMaxCat + j];
-    gen_path_codes<K>(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
+    const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
+    if constexpr (K == 2) {
+        const uint32_t c2[2] = {cnt[0], cnt[1]};
+        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, kBlock);
+    } else {
+        gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
+    }
     for (int t = 0; t < a.g.L; t++) {
         const uint32_t code = (codes[(t >> 3) * kBlock + tid] >> (4 * (t & 7))) & 15u;
         values[local * a.g.L + t] = a.g.tab[code].v1;

@@ -587,8 +587,7 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
         k_sequences<KK><<<grid, kBlock, smem, h->stream>>>(a, h->d_values);                                                   \
     } while (0)
     if (a.g.K <= 2) LAUNCH_SEQ(2);
-    else if (a.g.K <= 4) LAUNCH_SEQ(4);
-    else LAUNCH_SEQ(8);
+    else LAUNCH_SEQ(16);
 #undef LAUNCH_SEQ
     CUDA_TRY(cudaGetLastError());
     h->timing.launches++;

@@ -34,8 +34,8 @@ static cudaError_t launch_k(const PathArgs &a, int block, cudaStream_t stream)
 template <int MODE>
 static cudaError_t launch_mode(const PathArgs &a, int block, cudaStream_t stream)
 {
-    if (a.g.K <= 2) return launch_k<2, MODE>(a, block, stream);
-    return launch_k<8, MODE>(a, block, stream);
+    if (a.g.K <= 2) return launch_k<2, MODE>(a, block, stream);  // two values: register urn
+    return launch_k<16, MODE>(a, block, stream);                // up to 16 values: Fisher-Yates in shared memory
 }
 
 }  // namespace mcts

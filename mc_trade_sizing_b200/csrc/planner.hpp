@@ -75,7 +75,7 @@ struct SpecBuilder {
         s.cat_loss = category(-loss);
         if (s.cat_win < 0 || s.cat_loss < 0 || g.n_seg >= kMaxSeg) {
             status = MCTS_EUNSUPPORTED;
-            err = "more than 8 distinct trade values in one run (register urn limit of this build)";
+            err = "more than 16 distinct trade values in one run (4-bit outcome codes)";
             return false;
         }
         g.seg[g.n_seg++] = s;
@@ -151,8 +151,18 @@ inline int build_spec(const mcts_params &p, GenSpec *out, std::string *err)
         for (int k = 0; k < g.K; k++) {
             const double v = g.val[k];
             const int win = v > 0;
-            const int code = ((win ? n_win++ : n_loss++) << 1) | win;
-            g.rank_codes |= (uint32_t)code << (4 * k);
+            const int idx = win ? n_win++ : n_loss++;
+            if (idx >= 8) {
+                *err = "more than 8 distinct positive or 8 distinct non-positive trade values in one run (4-bit outcome codes)";
+                return MCTS_EUNSUPPORTED;
+            }
+            if (v != 0.0 && !(fabs(v) >= 4.450147717014403e-308 && fabs(v) <= 8.98846567431158e+307)) {
+                *err = "trade values must be 0 or between 2^-1021 and 2^1023 in magnitude in simulate mode (use replay for such inputs)";
+                return MCTS_EUNSUPPORTED;
+            }
+            const int code = (idx << 1) | win;
+            if (k < 8) g.rank_codes |= (uint32_t)code << (4 * k);
+            else g.rank_codes_hi |= (uint32_t)code << (4 * (k - 8));
             g.tab[code].v1 = v;
             g.tab[code].v2 = v * 2.0;
             g.tab[code].v3 = v * 3.0;

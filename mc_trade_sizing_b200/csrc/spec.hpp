@@ -2,7 +2,7 @@
 //
 // A run of run_all_strategies (reference: src/trading_models.py:445-530) is lowered on the host
 // to a GenSpec: the generator (:43-128) becomes either a list of iid Bernoulli segments or a
-// Markov chain over integer thresholds, and the <= 8 distinct trade values become "categories"
+// Markov chain over integer thresholds, and the <= 16 distinct trade values become "categories"
 // whose 4-bit codes (bit 0 = "value > 0", the win test of :154) are what the path kernel keeps
 // per trade in shared memory.
 #pragma once
@@ -17,7 +17,7 @@
 namespace mcts {
 
 constexpr int kNumStrategies = 20;
-constexpr int kMaxCat = 8;        // distinct trade values per run handled by the register urn
+constexpr int kMaxCat = 16;       // distinct trade values per run (4-bit codes: <= 8 positive and <= 8 non-positive)
 constexpr int kMaxSeg = 20;       // 16 regimes, or the 3 phases + tail fill of :44-65
 constexpr int kMaxStackDepth = 12; // pairwise-tree depth over trades: T <= 128 * 2^11
 constexpr int kMaxLeaves = 512;
@@ -45,7 +45,9 @@ struct GenSpec {
     uint64_t thr1[2];    // Markov-1: [after loss, after win] (:75-79)
     uint64_t thr2[4];    // Markov-2: index = older*2 + newer (:93-100)
     int32_t cat_win, cat_loss;  // Markov modes
-    uint32_t rank_codes;        // nibble r = 4-bit code of category r
+    uint32_t rank_codes;        // nibble r = 4-bit code of category r (r < 8)
+    uint32_t rank_codes_hi;     // categories 8..15
+    int32_t pad0;
     int32_t all_int;            // every value integral and 6*max|v|*L < 2^31
     double val[kMaxCat];
     Tab tab[16];                // indexed by code

@@ -84,8 +84,7 @@ int h_simulate(const mcts_params *p, uint64_t seed, int dedup, double *profit, d
         uint32_t cnt[kMaxCat];
         gen_base_counts(g, seed, (uint32_t)sim, cnt);
         if (g.K <= 2) gen_path_codes<2>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
-        else if (g.K <= 4) gen_path_codes<4>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
-        else gen_path_codes<8>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
+        else gen_path_codes_fy(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
         if (seqs)
             for (int t = 0; t < g.L; t++) seqs[i * g.L + t] = g.tab[(codes[t >> 3] >> (4 * (t & 7))) & 15].v1;
         if (profit) {

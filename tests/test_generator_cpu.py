@@ -40,7 +40,7 @@ def test_base_counts_follow_the_generator_laws():
     """Mean win counts per category over many simulations vs the chains' exact expectations."""
     n = 4000
     prm = make_params(0.82, 186.0, 219.0, 1000, n, 1)
-    acc = np.zeros(8)
+    acc = np.zeros(16)
     for sim in range(n):
         c, vals, L = harness.base_counts(prm, 99, sim)
         assert c.sum() == 1000 and L == 1000

@@ -93,7 +93,9 @@ typedef struct {
     int32_t int_fast_path; /* 0 = fp64 evaluator always; 1 = allow the exact int32 evaluator when
                               every trade value is an integer and sums stay below 2^31 */
     int32_t block_threads; /* 0 = default */
-    int32_t reserved;
+    int32_t serial_chunks; /* 0 = default: consecutive chunks run on two streams so the reduction and the
+                              wave tail of one overlap the path kernel of the next; 1 = one stream (clean
+                              per-kernel event timing for roofline measurements) */
 } mcts_options;
 
 /* Device-side timing of the last call on a handle (CUDA events on the library's stream). */

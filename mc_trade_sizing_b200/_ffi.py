@@ -39,7 +39,7 @@ class Agg(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("chunk_paths", C.c_int64), ("dedup", C.c_int32), ("int_fast_path", C.c_int32),
-                ("block_threads", C.c_int32), ("reserved", C.c_int32)]
+                ("block_threads", C.c_int32), ("serial_chunks", C.c_int32)]
 
 
 class Timing(C.Structure):

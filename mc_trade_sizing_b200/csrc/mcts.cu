@@ -42,14 +42,20 @@ struct mcts_handle {
     int device = 0;
     int sm_count = 0;
     int block_threads = 0;  // experiment override (mcts_options.block_threads)
-    cudaStream_t stream = nullptr;
-    // device buffers (grow-only)
-    uint32_t *d_counts = nullptr;
-    int64_t cap_sims = 0;
-    double *d_out = nullptr;
-    int64_t cap_paths = 0;
-    double *d_part = nullptr;
-    int64_t cap_part = 0;  // pstride
+    // Two lanes (stream + scratch buffers): consecutive chunks alternate between them so that the
+    // memory-bound reduction and the wave tail of one chunk overlap the issue-bound path kernel of the
+    // next.  lane[0].stream is "the" stream of the handle (mcts_get_stream).
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        uint32_t *d_counts = nullptr;
+        int64_t cap_sims = 0;
+        double *d_out = nullptr;
+        int64_t cap_paths = 0;
+        double *d_part = nullptr;
+        int64_t cap_part = 0;  // 120 * pstride
+        cudaEvent_t done = nullptr;
+    } lane[2];
+    cudaStream_t stream = nullptr;  // == lane[0].stream
     mcts_chunk_result *d_recs = nullptr;
     int64_t cap_recs = 0;
     LeafSched *d_sched = nullptr;
@@ -75,7 +81,9 @@ static int get_event(mcts_handle *h, cudaEvent_t *e)
     return MCTS_OK;
 }
 
-static int mark(mcts_handle *h, std::vector<EventPair> &v, bool begin)
+typedef mcts_handle::Lane Lane;
+
+static int mark(mcts_handle *h, cudaStream_t stream, std::vector<EventPair> &v, bool begin)
 {
     if (begin) {
         EventPair p;
@@ -84,9 +92,9 @@ static int mark(mcts_handle *h, std::vector<EventPair> &v, bool begin)
         rc = get_event(h, &p.b);
         if (rc) return rc;
         v.push_back(p);
-        CUDA_TRY(cudaEventRecord(p.a, h->stream));
+        CUDA_TRY(cudaEventRecord(p.a, stream));
     } else {
-        CUDA_TRY(cudaEventRecord(v.back().b, h->stream));
+        CUDA_TRY(cudaEventRecord(v.back().b, stream));
     }
     return MCTS_OK;
 }
@@ -172,7 +180,11 @@ int mcts_create(int device, mcts_handle **out)
     if (!h) return fail(MCTS_ENOMEM, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &L : h->lane) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    }
+    h->stream = h->lane[0].stream;
     CUDA_TRY(cudaEventCreate(&h->ev_begin));
     CUDA_TRY(cudaEventCreate(&h->ev_end));
     CUDA_TRY(cudaMalloc(&h->d_sched, sizeof(LeafSched)));
@@ -185,17 +197,21 @@ void mcts_destroy(mcts_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_counts);
-    cudaFree(h->d_out);
-    cudaFree(h->d_part);
+    for (auto &L : h->lane) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        cudaFree(L.d_counts);
+        cudaFree(L.d_out);
+        cudaFree(L.d_part);
+        if (L.done) cudaEventDestroy(L.done);
+    }
     cudaFree(h->d_recs);
     cudaFree(h->d_sched);
     cudaFree(h->d_values);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (auto &L : h->lane)
+        if (L.stream) cudaStreamDestroy(L.stream);
     delete h;
 }
 
@@ -345,61 +361,82 @@ static int pick_block(int L, int want)
     return 0;
 }
 
-static int launch_paths(mcts_handle *h, int mode, const PathArgs &a)
+static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
 {
     const int block = pick_block(a.g.L, h->block_threads);
     if (!block) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~14000 trades)");
     cudaError_t e;
     switch (mode) {
-        case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, h->stream); break;
-        case PM_CURVES: e = mcts_launch_paths_curves(a, block, h->stream); break;
-        default: e = mcts_launch_paths_full(a, block, h->stream); break;
+        case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, L.stream); break;
+        case PM_CURVES: e = mcts_launch_paths_curves(a, block, L.stream); break;
+        default: e = mcts_launch_paths_full(a, block, L.stream); break;
     }
     if (e != cudaSuccess) return fail(MCTS_ECUDA, std::string("k_sim_paths launch failed: ") + cudaGetErrorString(e));
     h->timing.launches++;
     return MCTS_OK;
 }
 
-static int launch_gen_base(mcts_handle *h, const GenSpec &g, uint64_t seed, int64_t sim0, int64_t n_sims)
+static int launch_gen_base(mcts_handle *h, Lane &L, const GenSpec &g, uint64_t seed, int64_t sim0, int64_t n_sims)
 {
-    int rc = ensure(&h->d_counts, &h->cap_sims, n_sims, sizeof(uint32_t) * kMaxCat);
+    int rc = ensure(&L.d_counts, &L.cap_sims, n_sims, sizeof(uint32_t) * kMaxCat);
     if (rc) return rc;
-    if ((rc = mark(h, h->ev_gen, true))) return rc;
-    k_gen_base<<<(unsigned)((n_sims + 127) / 128), 128, 0, h->stream>>>(g, seed, sim0, n_sims, h->d_counts);
+    if ((rc = mark(h, L.stream, h->ev_gen, true))) return rc;
+    k_gen_base<<<(unsigned)((n_sims + 127) / 128), 128, 0, L.stream>>>(g, seed, sim0, n_sims, L.d_counts);
     CUDA_TRY(cudaGetLastError());
     h->timing.launches++;
-    return mark(h, h->ev_gen, false);
+    return mark(h, L.stream, h->ev_gen, false);
 }
 
 // reduce the [40][ld] per-path rows of one chunk into one record
-static int launch_reduce(mcts_handle *h, int64_t n, int64_t first_path, mcts_chunk_result *d_rec)
+static int launch_reduce(mcts_handle *h, Lane &L, int64_t n, int64_t first_path, mcts_chunk_result *d_rec)
 {
     const int d = reduce_depth(n);
     const int64_t nodes = (int64_t)1 << d;
-    int rc = ensure(&h->d_part, &h->cap_part, std::max<int64_t>(nodes, 1024) * 120);
+    int rc = ensure(&L.d_part, &L.cap_part, std::max<int64_t>(nodes, 1024) * 120);
     if (rc) return rc;
-    const int64_t pstride = h->cap_part / 120;
-    if ((rc = mark(h, h->ev_reduce, true))) return rc;
+    const int64_t pstride = L.cap_part / 120;
+    if ((rc = mark(h, L.stream, h->ev_reduce, true))) return rc;
     dim3 grid((unsigned)((nodes + 127) / 128), 40);
-    k_reduce_nodes<<<grid, 128, 0, h->stream>>>(h->d_out, h->cap_paths, n, d, h->d_part, pstride);
+    k_reduce_nodes<<<grid, 128, 0, L.stream>>>(L.d_out, L.cap_paths, n, d, L.d_part, pstride);
     CUDA_TRY(cudaGetLastError());
-    k_reduce_top<<<1, 64, 0, h->stream>>>(h->d_part, pstride, d, d_rec, first_path, n);
+    k_reduce_top<<<1, 64, 0, L.stream>>>(L.d_part, pstride, d, d_rec, first_path, n);
     CUDA_TRY(cudaGetLastError());
     h->timing.launches += 2;
-    return mark(h, h->ev_reduce, false);
+    return mark(h, L.stream, h->ev_reduce, false);
 }
 
-static int copy_paths_out(mcts_handle *h, int64_t first, int64_t n, int64_t P, double *profit, double *dd)
+static int ensure_out(Lane &L, int64_t max_n)
+{
+    if (max_n <= L.cap_paths) return MCTS_OK;
+    return ensure(&L.d_out, &L.cap_paths, (max_n + 7) / 8 * 8, sizeof(double) * 40);  // rows stay 64-byte aligned
+}
+
+// lane 1 starts after everything already queued on lane 0 (the handle's stream) ...
+static int fork_lanes(mcts_handle *h)
+{
+    CUDA_TRY(cudaEventRecord(h->ev_begin, h->lane[0].stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->lane[1].stream, h->ev_begin, 0));
+    return MCTS_OK;
+}
+// ... and lane 0 ends after lane 1, so events recorded on the handle's stream bracket the whole call
+static int join_lanes(mcts_handle *h)
+{
+    CUDA_TRY(cudaEventRecord(h->lane[1].done, h->lane[1].stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->lane[0].stream, h->lane[1].done, 0));
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->lane[0].stream));
+    return MCTS_OK;
+}
+
+static int copy_paths_out(mcts_handle *h, Lane &L, int64_t first, int64_t n, int64_t P, double *profit, double *dd)
 {
     if (profit) {
-        CUDA_TRY(cudaMemcpy2DAsync(profit + first, (size_t)P * 8, h->d_out, (size_t)h->cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(profit + first, (size_t)P * 8, L.d_out, (size_t)L.cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, L.stream));
         h->timing.d2h_bytes += n * 8 * 20;
     }
     if (dd) {
-        CUDA_TRY(cudaMemcpy2DAsync(dd + first, (size_t)P * 8, h->d_out + 20 * h->cap_paths, (size_t)h->cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(dd + first, (size_t)P * 8, L.d_out + 20 * L.cap_paths, (size_t)L.cap_paths * 8, (size_t)n * 8, 20, cudaMemcpyDeviceToHost, L.stream));
         h->timing.d2h_bytes += n * 8 * 20;
     }
-    if (profit || dd) CUDA_TRY(cudaStreamSynchronize(h->stream));  // d_out is reused by the next chunk
     return MCTS_OK;
 }
 
@@ -424,15 +461,16 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
     int64_t max_n = 0;
     for (int64_t c = cb; c < ce; c++) max_n = std::max(max_n, count[c]);
     if (max_n == 0) return MCTS_OK;
-    if (max_n > h->cap_paths) {  // rows must keep 64-byte alignment for the reduction's vector loads
-        if ((rc = ensure(&h->d_out, &h->cap_paths, (max_n + 7) / 8 * 8, sizeof(double) * 40))) return rc;
-    }
+    const int n_lanes = (opt && opt->serial_chunks) || ce - cb < 2 ? 1 : 2;
+    for (int l = 0; l < n_lanes; l++)
+        if ((rc = ensure_out(h->lane[l], max_n))) return rc;
     if ((rc = ensure(&h->d_recs, &h->cap_recs, ce - cb))) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    if ((rc = fork_lanes(h))) return rc;
     for (int64_t c = cb; c < ce; c++) {
+        Lane &L = h->lane[(c - cb) % n_lanes];
         const int64_t f = first[c], n = count[c];
         const int64_t s_lo = f / p->num_mc_shuffles, s_hi = (f + n - 1) / p->num_mc_shuffles;
-        if ((rc = launch_gen_base(h, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
+        if ((rc = launch_gen_base(h, L, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
         PathArgs a;
         memset(&a, 0, sizeof a);
         a.g = g;
@@ -441,19 +479,19 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
         a.n = n;
         a.sim0 = s_lo;
         a.n_sh = p->num_mc_shuffles;
-        a.counts = h->d_counts;
+        a.counts = L.d_counts;
         a.sched = h->d_sched;
-        a.out = h->d_out;
-        a.ld = h->cap_paths;
-        if ((rc = mark(h, h->ev_paths, true))) return rc;
-        rc = launch_paths(h, mode, a);
+        a.out = L.d_out;
+        a.ld = L.cap_paths;
+        if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
+        rc = launch_paths(h, L, mode, a);
         if (rc) return rc;
-        if ((rc = mark(h, h->ev_paths, false))) return rc;
-        if ((rc = launch_reduce(h, n, f, h->d_recs + (c - cb)))) return rc;
-        if ((rc = copy_paths_out(h, f, n, P, profit, dd))) return rc;
+        if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
+        if ((rc = launch_reduce(h, L, n, f, h->d_recs + (c - cb)))) return rc;
+        if ((rc = copy_paths_out(h, L, f, n, P, profit, dd))) return rc;
         h->timing.trade_steps += n * (int64_t)g.L * MCTS_NSTRAT;
     }
-    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    if ((rc = join_lanes(h))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, h->d_recs, sizeof(mcts_chunk_result) * (size_t)(ce - cb), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * (ce - cb);
@@ -499,7 +537,8 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
     int rc;
     if ((rc = upload_sched(h, T))) return rc;
     int64_t max_n = *std::max_element(count.begin(), count.end());
-    if (max_n > h->cap_paths && (rc = ensure(&h->d_out, &h->cap_paths, (max_n + 7) / 8 * 8, sizeof(double) * 40))) return rc;
+    Lane &L = h->lane[0];
+    if ((rc = ensure_out(L, max_n))) return rc;
     if ((rc = ensure(&h->d_values, &h->cap_values, max_n * T))) return rc;
     if ((rc = ensure(&h->d_recs, &h->cap_recs, nc))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
@@ -513,10 +552,10 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
         a.path0 = f;
         a.n = n;
         a.sched = h->d_sched;
-        a.out = h->d_out;
-        a.ld = h->cap_paths;
+        a.out = L.d_out;
+        a.ld = L.cap_paths;
         const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
-        if ((rc = mark(h, h->ev_paths, true))) return rc;
+        if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
         if (mode == PM_DEDUP) {
             k_replay_pass<DedupPass0, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
             k_replay_pass<DedupPass1, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
@@ -530,9 +569,9 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
             h->timing.launches += 4;
         }
         CUDA_TRY(cudaGetLastError());
-        if ((rc = mark(h, h->ev_paths, false))) return rc;
-        if ((rc = launch_reduce(h, n, f, h->d_recs + c))) return rc;
-        if ((rc = copy_paths_out(h, f, n, P, profit, dd))) return rc;
+        if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
+        if ((rc = launch_reduce(h, L, n, f, h->d_recs + c))) return rc;
+        if ((rc = copy_paths_out(h, L, f, n, P, profit, dd))) return rc;
         h->timing.trade_steps += n * T * MCTS_NSTRAT;
     }
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
@@ -556,7 +595,7 @@ static int path_range_args(mcts_handle *h, const mcts_params *p, uint64_t seed, 
     if ((rc = upload_sched(h, g.L))) return rc;
     const int64_t s_lo = first_path / p->num_mc_shuffles, s_hi = (first_path + n - 1) / p->num_mc_shuffles;
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    if ((rc = launch_gen_base(h, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
+    if ((rc = launch_gen_base(h, h->lane[0], g, seed, s_lo, s_hi - s_lo + 1))) return rc;
     memset(a, 0, sizeof *a);
     a->g = g;
     a->seed = seed;
@@ -564,7 +603,7 @@ static int path_range_args(mcts_handle *h, const mcts_params *p, uint64_t seed, 
     a->n = n;
     a->sim0 = s_lo;
     a->n_sh = p->num_mc_shuffles;
-    a->counts = h->d_counts;
+    a->counts = h->lane[0].d_counts;
     a->sched = h->d_sched;
     return MCTS_OK;
 }
@@ -607,9 +646,9 @@ int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int6
     if (rc) return rc;
     a.curves = curves_dev;
     a.out = nullptr;
-    if ((rc = mark(h, h->ev_paths, true))) return rc;
-    if ((rc = launch_paths(h, PM_CURVES, a))) return rc;
-    if ((rc = mark(h, h->ev_paths, false))) return rc;
+    if ((rc = mark(h, h->stream, h->ev_paths, true))) return rc;
+    if ((rc = launch_paths(h, h->lane[0], PM_CURVES, a))) return rc;
+    if ((rc = mark(h, h->stream, h->ev_paths, false))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->timing.trade_steps = n * (int64_t)a.g.L * MCTS_NSTRAT;

@@ -86,8 +86,8 @@ class Engine:
         self.close()
 
     @staticmethod
-    def options(chunk_paths=0, dedup=False, int_fast_path=False, block_threads=0) -> Options:
-        return Options(int(chunk_paths), int(bool(dedup)), int(bool(int_fast_path)), int(block_threads), 0)
+    def options(chunk_paths=0, dedup=False, int_fast_path=False, block_threads=0, serial_chunks=False) -> Options:
+        return Options(int(chunk_paths), int(bool(dedup)), int(bool(int_fast_path)), int(block_threads), int(bool(serial_chunks)))
 
     # -- on-device RNG ------------------------------------------------------------------------
     def simulate(self, params: Params, seed: int = DEFAULT_SEED, per_path: bool = False, options: Options | None = None):

@@ -74,6 +74,10 @@ def lib():
         L.oracle_np_sum.argtypes = [dp, C.c_int64]
         L.oracle_rng_taps.restype = None
         L.oracle_rng_taps.argtypes = [C.c_uint32, C.c_int, dp, C.c_int, dp]
+        L.devgen_sequences.restype = C.c_int64
+        L.devgen_sequences.argtypes = [C.POINTER(Params), C.c_uint64, C.c_int64, C.c_int64, dp]
+        L.devgen_philox.restype = None
+        L.devgen_philox.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.oracle_bench.restype = C.c_double
         L.oracle_bench.argtypes = [C.POINTER(Params), C.c_uint32, C.c_int, dp]
         _lib = L
@@ -177,3 +181,24 @@ def bench(params: Params, seed0: int, n_threads: int) -> float:
     if secs < 0:
         raise RuntimeError("oracle bench failed")
     return secs
+
+
+def devgen_sequences(params: Params, seed: int, first_path: int = 0, n: int | None = None) -> np.ndarray:
+    """Independent CPU restatement (oracle/devgen_ref.c) of the DEVICE generator specification:
+    the post-shuffle sequences mcts_simulate evaluates for paths [first_path, first_path+n)."""
+    P = params.num_simulations * params.num_mc_shuffles
+    n = P - first_path if n is None else n
+    Lseq = sequence_length(params)
+    out = np.zeros((max(n, 0), max(Lseq, 0)))
+    rc = lib().devgen_sequences(C.byref(params), C.c_uint64(seed & (2**64 - 1)), int(first_path), int(n), _dp(out))
+    if rc < 0:
+        raise ValueError("devgen: invalid probabilities (NumPy's choice() would raise)")
+    assert rc == Lseq or n == 0, (rc, Lseq)
+    return out
+
+
+def devgen_philox(key, ctr):
+    c = (C.c_uint32 * 4)(*ctr)
+    o = (C.c_uint32 * 4)()
+    lib().devgen_philox(key[0], key[1], c, o)
+    return list(o)

@@ -91,3 +91,31 @@ def test_simulated_paths_evaluate_like_the_reference():
             ref = oracle.eval_paths(out["seqs"])
             assert_bitexact(out["profit"], ref["profit"], "%s T=%d profit" % (mode, T))
             assert_bitexact(out["dd"], ref["dd"], "%s T=%d dd" % (mode, T))
+
+
+def test_device_generator_code_matches_independent_restatement():
+    """csrc/gen_core.cuh (compiled for the host) vs oracle/devgen_ref.c, written from the spec: base
+    multiset laws, category order, Fisher-Yates / urn shuffle, counter layout -- bit for bit."""
+    assert oracle.devgen_philox((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    many = [{"length": 40 + 3 * i, "hit_rate": 0.3 + 0.04 * i, "avg_win": 50.0 + 10 * i, "avg_loss": 20.5 + 7 * i} for i in range(7)]
+    cases = []
+    for mode, kw in MODE_KW.items():
+        for T in (1000, 129, 37, 9, 8, 5, 2, 1):
+            kw2 = dict(kw)
+            if mode == "regime" and T != 1000:
+                kw2["regimes"] = None
+            cases.append(((0.82, 186.0, 219.0, T, 4, 3), kw2))
+    cases.append(((0.6, 186.3, 219.7, 500, 3, 3), MODE_KW["markov1"]))
+    cases.append(((0.82, 186.0, 219.0, 1200, 2, 3), MODE_KW["regime"]))
+    cases.append(((0.82, 186.0, 219.0, 450, 2, 3), MODE_KW["regime"]))
+    cases.append(((0.82, 186.0, 219.0, 400, 3, 2), dict(use_regime=True, regimes=many)))      # 14 distinct values
+    cases.append(((0.2, 50.0, 75.5, 333, 3, 4), {}))
+    cases.append(((0.5, 10.0, -10.0, 50, 3, 2), dict(use_markov=True)))                           # one distinct value
+    for args, kw in cases:
+        for seed in (12345, 2**63 + 11):
+            dev = harness.simulate(make_params(*args, **kw), seed, want_eval=False)["seqs"]
+            ref = oracle.devgen_sequences(oracle.make_params(*args, **kw), seed)
+            assert_bitexact(dev, ref, "%s %s" % (args, list(kw)))
+    prm = oracle.make_params(0.82, 186.0, 219.0, 203, 9, 7)
+    assert_bitexact(oracle.devgen_sequences(prm, 5, first_path=17, n=30), oracle.devgen_sequences(prm, 5)[17:47])

@@ -146,6 +146,21 @@ def test_device_generator_matches_its_cpu_model(eng):
             assert_bitexact(part, dev[3:P - 2], name + " sub-range")
 
 
+def test_device_generator_matches_independent_restatement(eng):
+    """GPU sequences == oracle/devgen_ref.c (plain C written from the generator specification)."""
+    many = [{"length": 40 + 3 * i, "hit_rate": 0.3 + 0.04 * i, "avg_win": 50.0 + 10 * i, "avg_loss": 20.5 + 7 * i} for i in range(7)]
+    cases = _sim_cases() + [("regime_14_values", (0.82, 186.0, 219.0, 400, 30, 5), dict(use_regime=True, regimes=many))]
+    for name, args, kw in cases:
+        dev = eng.sequences(make_params(*args, **kw), seed=31337)
+        ref = oracle.devgen_sequences(oracle.make_params(*args, **kw), 31337)
+        assert_bitexact(dev, ref, name)
+        out = eng.simulate(make_params(*args, **kw), seed=31337, per_path=True)
+        exp = oracle.eval_paths(ref, num_trades=args[3])
+        assert_bitexact(out["profit"], exp["profit"], name + " profit")
+        assert_bitexact(out["dd"], exp["dd"], name + " dd")
+        assert_bitexact(out["summary"], exp["summary"], name + " summary")
+
+
 def test_sequences_are_permutations_of_one_multiset_per_simulation(eng):
     prm = make_params(0.82, 186.0, 219.0, 1000, 6, 5)
     seqs = eng.sequences(prm, seed=5)

@@ -287,6 +287,92 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
     }
 }
 
+// ---- exact int32 evaluator -----------------------------------------------------------------------
+// When every trade value is an integer and 6 * max|v| * L < 2^31 (checked on the host), equity, peak
+// and drawdown are exact integers below 2^30 in magnitude, every summation order gives the same
+// value (profit == final equity) and the fp64 results of the reference are reproduced exactly by
+// converting the int32 results at the end.  Five integer instructions per trade-step instead of
+// eleven fp64/select instructions; same masks, same rules.
+struct IntTab {
+    int32_t v1, v2, v3, pad;
+};
+
+template <int RULE>
+MCTS_HD int32_t contribution_i(const Masks &m, uint32_t bit, int32_t v1, int32_t v2, int32_t v3)
+{
+    if constexpr (RULE == R_C1) return v1;
+    if constexpr (RULE == R_AM) return (m.pw & bit) ? v2 : v1;
+    if constexpr (RULE == R_F1) return (m.fw & bit) ? v2 : v1;
+    if constexpr (RULE == R_MG) return (m.pl & bit) ? v2 : v1;
+    if constexpr (RULE == R_MG2) return (m.pll & bit) ? v2 : v1;
+    if constexpr (RULE == R_P1) return (m.pw & bit) ? 0 : v1;
+    if constexpr (RULE == R_P2) return (m.pww & bit) ? 0 : v1;
+    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0 : ((m.s16 & bit) ? v2 : v1);
+    if constexpr (RULE == R_S18) return (m.pww & bit) ? v3 : v1;
+    if constexpr (RULE == R_S19) return (m.pll & bit) ? v3 : ((m.pww & bit) ? v2 : v1);
+    if constexpr (RULE == R_S20) return (m.pll & bit) ? v3 : v1;
+    return v1;
+}
+
+MCTS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+MCTS_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+
+template <class IDS>
+MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab, int L, int32_t (&profit)[IDS::N], int32_t (&drawdown)[IDS::N])
+{
+    constexpr int NS = IDS::N;
+    int32_t E[NS], peak[NS], dd[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        E[s] = 0;
+        peak[s] = -(1 << 30);  // below any reachable equity; E_0 - peak cannot overflow
+        dd[s] = 0;
+    }
+    History h;
+    h.w = 0;
+    h.l = 0;
+    const int n_oct = L >> 3, tail = L & 7;
+    for (int oct = 0; oct < n_oct; oct++) {
+        const uint32_t word = codes[(size_t)oct * stride];
+        const uint32_t W = word & 0x11111111u;
+        const Masks m = make_masks(W, W ^ 0x11111111u, h);
+        static_for<8>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const IntTab t = tab[(word >> (4 * i)) & 15u];
+            constexpr uint32_t bit = mask_bit(i);
+            static_for<NS>([&](auto S) {
+                constexpr int s = decltype(S)::value;
+                constexpr int rule = rule_of_id(IDS::id(s));
+                E[s] += contribution_i<rule>(m, bit, t.v1, t.v2, t.v3);
+                dd[s] = imin(dd[s], E[s] - peak[s]);
+                peak[s] = imax(peak[s], E[s]);
+            });
+        });
+    }
+    if (tail) {
+        const uint32_t word = codes[(size_t)n_oct * stride];
+        const uint32_t valid = 0x11111111u & ((1u << (4 * tail)) - 1u);
+        const uint32_t W = word & valid;
+        const Masks m = make_masks(W, W ^ valid, h);
+        for (int i = 0; i < tail; i++) {
+            const IntTab t = tab[(word >> (4 * i)) & 15u];
+            const uint32_t bit = mask_bit(i);
+            static_for<NS>([&](auto S) {
+                constexpr int s = decltype(S)::value;
+                constexpr int rule = rule_of_id(IDS::id(s));
+                E[s] += contribution_i<rule>(m, bit, t.v1, t.v2, t.v3);
+                dd[s] = imin(dd[s], E[s] - peak[s]);
+                peak[s] = imax(peak[s], E[s]);
+            });
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        profit[s] = E[s];
+        drawdown[s] = dd[s];
+    }
+}
+
 // ---- value sources ----------------------------------------------------------------------------
 
 // categorical: 8 trades per 32-bit word, 4-bit code each; code -> {v, 2v, fl(3v)} table

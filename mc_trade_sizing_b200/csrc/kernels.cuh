@@ -166,6 +166,80 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
     }
 }
 
+// ---- exact int32 variant of the hot kernel (all-integer runs: Markov defaults, README regimes) -----
+template <class IDS, int MODE>
+__device__ __forceinline__ void run_pass_int(const uint32_t *codes, int stride, const IntTab *tab, const PathArgs &a, int64_t local)
+{
+    int32_t profit[IDS::N], dd[IDS::N];
+    eval_path_int<IDS>(codes, stride, tab, a.g.L, profit, dd);
+    static_for<IDS::N>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        constexpr int id = IDS::id(s);
+        if constexpr (MODE == PM_DEDUP) {
+#pragma unroll
+            for (int other = 1; other <= kNumStrategies; other++) {
+                if (rule_of_id(other) == rule_of_id(id)) {
+                    a.out[(int64_t)(other - 1) * a.ld + local] = (double)profit[s];
+                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + local] = (double)dd[s];
+                }
+            }
+        } else {
+            a.out[(int64_t)(id - 1) * a.ld + local] = (double)profit[s];
+            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + local] = (double)dd[s];
+        }
+    });
+}
+
+template <int K, int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(const __grid_constant__ PathArgs a)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    IntTab *tab = reinterpret_cast<IntTab *>(smem);
+    uint32_t *codes = smem + kTabWords;
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        const int32_t v = a.g.ival[tid];
+        IntTab t;
+        t.v1 = v;
+        t.v2 = 2 * v;
+        t.v3 = 3 * v;
+        t.pad = 0;
+        tab[tid] = t;
+    }
+    __syncthreads();
+    const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
+    const bool active = local < a.n;
+    if (active) {
+        const int64_t path = a.path0 + local;
+        const int64_t sim = path / a.n_sh;
+        const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+        const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
+        if constexpr (K == 2) {
+            const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
+            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, BLOCK);
+        } else {
+            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
+        }
+    }
+    if constexpr (MODE == PM_DEDUP) {
+        __syncthreads();
+        if (active) run_pass_int<DedupPass0, MODE>(codes + tid, BLOCK, tab, a, local);
+        __syncthreads();
+        if (active) run_pass_int<DedupPass1, MODE>(codes + tid, BLOCK, tab, a, local);
+        __syncthreads();
+        if (active) run_pass_int<DedupPass2, MODE>(codes + tid, BLOCK, tab, a, local);
+    } else {
+        __syncthreads();
+        if (active) run_pass_int<FullPass0, MODE>(codes + tid, BLOCK, tab, a, local);
+        __syncthreads();
+        if (active) run_pass_int<FullPass1, MODE>(codes + tid, BLOCK, tab, a, local);
+        __syncthreads();
+        if (active) run_pass_int<FullPass2, MODE>(codes + tid, BLOCK, tab, a, local);
+        __syncthreads();
+        if (active) run_pass_int<FullPass3, MODE>(codes + tid, BLOCK, tab, a, local);
+    }
+}
+
 // replay: values [n][T] row-major fp64 in device memory, one pass (five strategies) per launch
 template <class IDS, int MODE>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __grid_constant__ PathArgs a, const double *__restrict__ values, int64_t T)

@@ -42,6 +42,7 @@ struct mcts_handle {
     int device = 0;
     int sm_count = 0;
     int block_threads = 0;  // experiment override (mcts_options.block_threads)
+    int int_fast_path = 0;  // mcts_options.int_fast_path
     // Two lanes (stream + scratch buffers): consecutive chunks alternate between them so that the
     // memory-bound reduction and the wave tail of one chunk overlap the issue-bound path kernel of the
     // next.  lane[0].stream is "the" stream of the handle (mcts_get_stream).
@@ -338,6 +339,8 @@ static size_t path_smem_bytes(int L, int block) { return (size_t)kTabWords * 4 +
 cudaError_t mcts_launch_paths_full(const PathArgs &a, int block, cudaStream_t stream);
 cudaError_t mcts_launch_paths_dedup(const PathArgs &a, int block, cudaStream_t stream);
 cudaError_t mcts_launch_paths_curves(const PathArgs &a, int block, cudaStream_t stream);
+cudaError_t mcts_launch_paths_int_full(const PathArgs &a, int block, cudaStream_t stream);
+cudaError_t mcts_launch_paths_int_dedup(const PathArgs &a, int block, cudaStream_t stream);
 
 // Block size: the largest of 128 / 64 / 32 that keeps at least 80 % of the best achievable number
 // of threads resident per SM given the shared-memory code columns (4 bits per trade per thread,
@@ -366,6 +369,12 @@ static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
     const int block = pick_block(a.g.L, h->block_threads);
     if (!block) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~14000 trades)");
     cudaError_t e;
+    if (h->int_fast_path && a.g.all_int && mode != PM_CURVES) {  // exact int32 evaluator, identical results
+        e = mode == PM_DEDUP ? mcts_launch_paths_int_dedup(a, block, L.stream) : mcts_launch_paths_int_full(a, block, L.stream);
+        if (e != cudaSuccess) return fail(MCTS_ECUDA, std::string("k_sim_paths_int launch failed: ") + cudaGetErrorString(e));
+        h->timing.launches++;
+        return MCTS_OK;
+    }
     switch (mode) {
         case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, L.stream); break;
         case PM_CURVES: e = mcts_launch_paths_curves(a, block, L.stream); break;
@@ -453,6 +462,7 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
     const int64_t chunk = clamp_chunk(opt ? opt->chunk_paths : 0);
     const int mode = (opt && opt->dedup) ? PM_DEDUP : PM_FULL;
     h->block_threads = opt ? opt->block_threads : 0;
+    h->int_fast_path = opt ? opt->int_fast_path : 0;
     std::vector<int64_t> first, count;
     plan_visit(0, P, chunk, &first, &count);
     if (cb < 0 || ce > (int64_t)first.size() || cb > ce) return fail(MCTS_EINVAL, "chunk range outside the plan");

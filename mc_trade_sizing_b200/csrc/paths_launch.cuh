@@ -40,5 +40,39 @@ static cudaError_t launch_mode(const PathArgs &a, int block, cudaStream_t stream
 
 }  // namespace mcts
 
+namespace mcts {
+template <int K, int MODE, int BLOCK>
+static cudaError_t launch_int_kb(const PathArgs &a, cudaStream_t stream)
+{
+    const size_t smem = path_smem_bytes(a.g.L, BLOCK);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_sim_paths_int<K, MODE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned grid = (unsigned)((a.n + BLOCK - 1) / BLOCK);
+    k_sim_paths_int<K, MODE, BLOCK><<<grid, BLOCK, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+template <int K, int MODE>
+static cudaError_t launch_int_k(const PathArgs &a, int block, cudaStream_t stream)
+{
+    switch (block) {
+        case 128: return launch_int_kb<K, MODE, 128>(a, stream);
+        case 64: return launch_int_kb<K, MODE, 64>(a, stream);
+        case 32: return launch_int_kb<K, MODE, 32>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+template <int MODE>
+static cudaError_t launch_int_mode(const PathArgs &a, int block, cudaStream_t stream)
+{
+    if (a.g.K <= 2) return launch_int_k<2, MODE>(a, block, stream);
+    return launch_int_k<16, MODE>(a, block, stream);
+}
+}  // namespace mcts
+
+#define MCTS_DEFINE_INT_LAUNCHER(NAME, MODE) \
+    cudaError_t NAME(const mcts::PathArgs &a, int block, cudaStream_t stream) { return mcts::launch_int_mode<MODE>(a, block, stream); }
+
 #define MCTS_DEFINE_PATH_LAUNCHER(NAME, MODE) \
     cudaError_t NAME(const mcts::PathArgs &a, int block, cudaStream_t stream) { return mcts::launch_mode<MODE>(a, block, stream); }

@@ -166,7 +166,7 @@ inline int build_spec(const mcts_params &p, GenSpec *out, std::string *err)
             g.tab[code].v1 = v;
             g.tab[code].v2 = v * 2.0;
             g.tab[code].v3 = v * 3.0;
-            if (!(fabs(v) <= 1e9) || v != floor(v)) g.all_int = 0;
+            if (!(fabs(v) <= 1e9) || v != floor(v) || (v == 0.0 && signbit(v))) g.all_int = 0;
             else g.ival[code] = (int32_t)v;
             if (fabs(v) > vmax) vmax = fabs(v);
         }

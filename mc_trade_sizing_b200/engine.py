@@ -86,7 +86,7 @@ class Engine:
         self.close()
 
     @staticmethod
-    def options(chunk_paths=0, dedup=False, int_fast_path=False, block_threads=0, serial_chunks=False) -> Options:
+    def options(chunk_paths=0, dedup=False, int_fast_path=True, block_threads=0, serial_chunks=False) -> Options:
         return Options(int(chunk_paths), int(bool(dedup)), int(bool(int_fast_path)), int(block_threads), int(bool(serial_chunks)))
 
     # -- on-device RNG ------------------------------------------------------------------------

@@ -49,6 +49,22 @@ static void run_all(SRC &src, const LeafSched *sch, int dedup, double *profit, d
     }
 }
 
+template <class IDS, bool DEDUP>
+static void run_pass_int(const uint32_t *codes, const IntTab *tab, int L, double *profit, double *dd, int64_t P, int64_t path)
+{
+    int32_t p[IDS::N], d[IDS::N];
+    eval_path_int<IDS>(codes, 1, tab, L, p, d);
+    for (int s = 0; s < IDS::N; s++) {
+        const int id = IDS::id(s);
+        for (int other = 1; other <= 20; other++) {
+            if (other == id || (DEDUP && rule_of_id(other) == rule_of_id(id))) {
+                profit[(int64_t)(other - 1) * P + path] = (double)p[s];
+                dd[(int64_t)(other - 1) * P + path] = (double)d[s];
+            }
+        }
+    }
+}
+
 extern "C" {
 
 // replay evaluator (ValueSource) on values[P][T]
@@ -67,8 +83,10 @@ int h_eval_values(const double *values, int64_t P, int64_t T, int dedup, double 
 
 // full simulate path on the host: spec -> base counts -> urn codes -> CodeSource evaluator.
 // seqs (optional) receives the decoded sequences [P][L].
-int h_simulate(const mcts_params *p, uint64_t seed, int dedup, double *profit, double *dd, double *seqs, int64_t first_path, int64_t n)
+// mode bit 0 = dedup, bit 1 = use the exact int32 evaluator when the run is all-integer
+int h_simulate(const mcts_params *p, uint64_t seed, int mode, double *profit, double *dd, double *seqs, int64_t first_path, int64_t n)
 {
+    const int dedup = mode & 1, want_int = mode & 2;
     GenSpec g;
     std::string err;
     int rc = build_spec(*p, &g, &err);
@@ -87,7 +105,20 @@ int h_simulate(const mcts_params *p, uint64_t seed, int dedup, double *profit, d
         else gen_path_codes_fy(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
         if (seqs)
             for (int t = 0; t < g.L; t++) seqs[i * g.L + t] = g.tab[(codes[t >> 3] >> (4 * (t & 7))) & 15].v1;
-        if (profit) {
+        if (profit && want_int && g.all_int) {
+            IntTab tab[16];
+            for (int c = 0; c < 16; c++) tab[c] = IntTab{g.ival[c], 2 * g.ival[c], 3 * g.ival[c], 0};
+            if (dedup) {
+                run_pass_int<DedupPass0, true>(codes.data(), tab, g.L, profit, dd, n, i);
+                run_pass_int<DedupPass1, true>(codes.data(), tab, g.L, profit, dd, n, i);
+                run_pass_int<DedupPass2, true>(codes.data(), tab, g.L, profit, dd, n, i);
+            } else {
+                run_pass_int<FullPass0, false>(codes.data(), tab, g.L, profit, dd, n, i);
+                run_pass_int<FullPass1, false>(codes.data(), tab, g.L, profit, dd, n, i);
+                run_pass_int<FullPass2, false>(codes.data(), tab, g.L, profit, dd, n, i);
+                run_pass_int<FullPass3, false>(codes.data(), tab, g.L, profit, dd, n, i);
+            }
+        } else if (profit) {
             CodeSource src;
             src.codes = codes.data();
             src.stride = 1;

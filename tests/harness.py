@@ -19,10 +19,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+        deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))]
         if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+            tmp = "%s.%d.tmp" % (LIB, os.getpid())   # atomic replace: several test processes may race here
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                            "-Wno-unknown-pragmas", "-o", LIB, SRC], check=True, capture_output=True)
+                            "-Wno-unknown-pragmas", "-o", tmp, SRC], check=True, capture_output=True)
+            os.replace(tmp, LIB)
         L = C.CDLL(LIB)
         dp = C.POINTER(C.c_double)
         L.h_eval_values.restype = C.c_int
@@ -55,14 +57,14 @@ def eval_values(values, dedup=False):
     return profit, dd
 
 
-def simulate(params, seed, first_path=0, n=None, dedup=False, want_eval=True):
+def simulate(params, seed, first_path=0, n=None, dedup=False, want_eval=True, int_path=False):
     P = params.num_simulations * params.num_mc_shuffles
     n = P - first_path if n is None else n
     L = int(_ffi.lib().mcts_sequence_length(C.byref(params)))
     profit = np.zeros((20, n)) if want_eval else None
     dd = np.zeros((20, n)) if want_eval else None
     seqs = np.zeros((n, L))
-    rc = lib().h_simulate(C.byref(params), C.c_uint64(seed), int(dedup), _dp(profit), _dp(dd), _dp(seqs), first_path, n)
+    rc = lib().h_simulate(C.byref(params), C.c_uint64(seed), int(dedup) | (2 if int_path else 0), _dp(profit), _dp(dd), _dp(seqs), first_path, n)
     if rc != 0:
         raise ValueError("harness rc %d" % rc)
     return {"profit": profit, "dd": dd, "seqs": seqs}

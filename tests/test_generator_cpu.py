@@ -119,3 +119,22 @@ def test_device_generator_code_matches_independent_restatement():
             assert_bitexact(dev, ref, "%s %s" % (args, list(kw)))
     prm = oracle.make_params(0.82, 186.0, 219.0, 203, 9, 7)
     assert_bitexact(oracle.devgen_sequences(prm, 5, first_path=17, n=30), oracle.devgen_sequences(prm, 5)[17:47])
+
+
+def test_int32_evaluator_is_exact_for_integer_runs():
+    """All-integer runs (Markov defaults, README regimes): the int32 evaluator must give the fp64 results."""
+    for mode in ("markov1", "markov2", "regime"):
+        for T in (1000, 129, 37, 8, 5, 1):
+            kw = dict(MODE_KW[mode])
+            if mode == "regime" and T != 1000:
+                kw["regimes"] = None
+            prm = make_params(0.82, 186.0, 219.0, T, 5, 4, **kw)
+            ref = oracle.eval_paths(harness.simulate(prm, 99, want_eval=False)["seqs"])
+            for dedup in (False, True):
+                out = harness.simulate(prm, 99, dedup=dedup, int_path=True)
+                assert_bitexact(out["profit"], ref["profit"], "%s T=%d int profit" % (mode, T))
+                assert_bitexact(out["dd"], ref["dd"], "%s T=%d int dd" % (mode, T))
+    # non-integer values silently stay on the fp64 path
+    prm = make_params(0.82, 186.0, 219.0, 100, 3, 2)
+    a, b = harness.simulate(prm, 1, int_path=True), harness.simulate(prm, 1)
+    assert_bitexact(a["profit"], b["profit"])

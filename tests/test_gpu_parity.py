@@ -126,10 +126,11 @@ def test_simulate_per_path_equals_oracle_on_device_sequences(eng):
             assert_bitexact(out["profit"], ref["profit"], name + " profit")
             assert_bitexact(out["dd"], ref["dd"], name + " dd")
             assert_bitexact(out["summary"], ref["summary"], name + " summary")
-            dd = eng.simulate(prm, seed=seed, per_path=True, options=eng.options(dedup=True))
-            assert_bitexact(dd["profit"], out["profit"], name + " dedup profit")
-            assert_bitexact(dd["dd"], out["dd"], name + " dedup dd")
-            assert_bitexact(dd["summary"], out["summary"], name + " dedup summary")
+            for opts in (eng.options(dedup=True), eng.options(int_fast_path=False), eng.options(dedup=True, int_fast_path=False)):
+                alt = eng.simulate(prm, seed=seed, per_path=True, options=opts)   # int32 / fp64 evaluators, 20 ids / 11 classes
+                assert_bitexact(alt["profit"], out["profit"], name + " variant profit")
+                assert_bitexact(alt["dd"], out["dd"], name + " variant dd")
+                assert_bitexact(alt["summary"], out["summary"], name + " variant summary")
 
 
 def test_device_generator_matches_its_cpu_model(eng):

@@ -15,6 +15,7 @@ ap.add_argument("--sims", type=int, default=104857)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--trades", type=int, default=1000)
 ap.add_argument("--block", type=int, default=0)
+ap.add_argument("--no-int", action="store_true")
 a = ap.parse_args()
 kw = {"dynamic": {}, "markov1": dict(use_markov=True, p_win_after_win=0.75, p_win_after_loss=0.60),
       "markov2": dict(use_markov2=True, p_win_ww=0.85, p_win_wl=0.65, p_win_lw=0.55, p_win_ll=0.30),
@@ -24,7 +25,7 @@ kw = {"dynamic": {}, "markov1": dict(use_markov=True, p_win_after_win=0.75, p_wi
 eng = Engine(0)
 prm = make_params(0.82, 186.0, 219.0, a.trades, a.sims, 20, **kw)
 for r in range(a.reps):
-    out = eng.simulate(prm, seed=100 + r, options=eng.options(chunk_paths=1 << 21, dedup=a.dedup, block_threads=a.block))
+    out = eng.simulate(prm, seed=100 + r, options=eng.options(chunk_paths=1 << 21, dedup=a.dedup, block_threads=a.block, int_fast_path=not a.no_int))
     t = eng.timing()
     print("rep %d: %.3f ms total, paths kernel %.3f ms, gen %.3f ms, reduce %.3f ms, %.4g trade-steps/s (kernel %.4g), avg_profit[1]=%.3f"
           % (r, t["total_ms"], t["paths_ms"], t["gen_ms"], t["reduce_ms"], t["trade_steps"] / t["total_ms"] * 1e3,

@@ -274,6 +274,22 @@ def main():
         eng.simulate(small, seed=2, options=o2)
         t = eng.timing()
         extras["dedup11_value"] = t["trade_steps"] / (t["total_ms"] * 1e-3)
+        # (a2) the other generator modes of BASELINE.json's configs (integer-valued -> exact int32 evaluator)
+        kws = {"markov1_c2": dict(use_markov=True, p_win_after_win=0.75, p_win_after_loss=0.60),
+               "markov2_c3": dict(use_markov2=True, p_win_ww=0.85, p_win_wl=0.65, p_win_lw=0.55, p_win_ll=0.30),
+               "regime_c4": dict(use_regime=True, regimes=[dict(length=300, hit_rate=0.9, avg_win=200, avg_loss=100),
+                                                           dict(length=200, hit_rate=0.5, avg_win=100, avg_loss=100),
+                                                           dict(length=500, hit_rate=0.2, avg_win=100, avg_loss=200)])}
+        extras["other_configs"] = {}
+        for name, kw in kws.items():
+            pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, SIMS_PER_GPU_STEP // 2, NUM_SHUFFLES, **kw)
+            for sd in (1, 2):
+                eng.simulate(pm, seed=sd, options=eng.options(chunk_paths=CHUNK_PATHS))
+            t = eng.timing()
+            eng.simulate(pm, seed=3, options=eng.options(chunk_paths=CHUNK_PATHS, int_fast_path=False))
+            t64 = eng.timing()
+            extras["other_configs"][name] = {"value": t["trade_steps"] / (t["total_ms"] * 1e-3),
+                                             "value_fp64_evaluator": t64["trade_steps"] / (t64["total_ms"] * 1e-3), "unit": UNIT}
         # (b) equity-curve export: HBM-bound, 8 B per trade-step
         n_curve = 1 << 17
         eng.export_curves(small, 3, 0, n_curve, to_host=False)

@@ -598,6 +598,50 @@ int oracle_eval_paths(const double *values, int64_t P, int64_t T, int num_trades
     return ORACLE_OK;
 }
 
+/*
+ * Equity curves (the np.cumsum temporaries of :136 / :167): curves[20][P][T], sequential fp64 prefix
+ * sums of each strategy's contributions.  Checker for the curve-export extension.
+ */
+int oracle_equity_curves(const double *values, int64_t P, int64_t T, double *curves)
+{
+    if (P <= 0 || T <= 0) return ORACLE_EEMPTY;
+    double *contrib = (double *)malloc(sizeof(double) * T);
+    if (!contrib) return ORACLE_ENOMEM;
+    for (int64_t path = 0; path < P; path++) {
+        const double *results = values + path * T;
+        for (int id = 1; id <= ORACLE_NSTRAT; id++) {
+            double *out = curves + ((int64_t)(id - 1) * P + path) * T;
+            if (id == 1) {
+                for (int64_t i = 0; i < T; i++) contrib[i] = results[i];
+            } else {
+                int size = 1;
+                strat_state st = {0, 0, 0, 0.0, 0.0};
+                for (int64_t i = 0; i < T; i++) {
+                    double trade_result = results[i] * (double)size;
+                    contrib[i] = st.paused ? 0.0 : trade_result;
+                    if (results[i] > 0) {
+                        st.win_streak += 1;
+                        st.loss_streak = 0;
+                    } else {
+                        st.loss_streak += 1;
+                        st.win_streak = 0;
+                    }
+                    st.last2_result = st.last_result;
+                    st.last_result = results[i];
+                    size = condition(id, results[i], size, &st);
+                }
+            }
+            double equity = 0;
+            for (int64_t i = 0; i < T; i++) {
+                equity = i == 0 ? contrib[0] : equity + contrib[i];
+                out[i] = equity;
+            }
+        }
+    }
+    free(contrib);
+    return ORACLE_OK;
+}
+
 /* Aggregate rows from per-path arrays only (np.mean/np.min/np.max restatement). */
 int oracle_summarise(const double *profit, const double *dd, int64_t P, int num_trades, double *summary)
 {

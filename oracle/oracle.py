@@ -68,6 +68,8 @@ def lib():
         L.oracle_run_all.argtypes = [C.POINTER(Params), C.c_uint32, dp, dp, dp, dp]
         L.oracle_eval_paths.restype = C.c_int
         L.oracle_eval_paths.argtypes = [dp, C.c_int64, C.c_int64, C.c_int, dp, dp, dp]
+        L.oracle_equity_curves.restype = C.c_int
+        L.oracle_equity_curves.argtypes = [dp, C.c_int64, C.c_int64, dp]
         L.oracle_summarise.restype = C.c_int
         L.oracle_summarise.argtypes = [dp, dp, C.c_int64, C.c_int, dp]
         L.oracle_np_sum.restype = C.c_double
@@ -153,6 +155,15 @@ def eval_paths(values: np.ndarray, num_trades: int | None = None):
     _check(lib().oracle_eval_paths(_dp(v), P, T, int(T if num_trades is None else num_trades),
                                    _dp(profit), _dp(dd), _dp(summary)))
     return {"profit": profit, "dd": dd, "summary": summary}
+
+
+def equity_curves(values: np.ndarray) -> np.ndarray:
+    """[20, P, T] equity curves (sequential cumsum of contributions) of caller-supplied sequences."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    P, T = v.shape
+    curves = np.zeros((NSTRAT, P, T))
+    _check(lib().oracle_equity_curves(_dp(v), P, T, _dp(curves)))
+    return curves
 
 
 def summarise(profit: np.ndarray, dd: np.ndarray, num_trades: int) -> np.ndarray:

@@ -261,6 +261,40 @@ def test_full_size_markov2_properties(eng):
     assert t["trade_steps"] == 1000000 * 1000 * 20 and t["launches"] > 0
 
 
+def test_full_size_regime_config_c4(eng):
+    """Config C4 at full size: 1e7 regime paths (README regimes).  Aggregates only (per-path arrays would
+    be 3.2 GB on the host); size-independent properties: independence of chunking and of the evaluator
+    (int32 vs fp64, 20 ids vs 11 classes), tie groups, bounds, analytic mean."""
+    prm = make_params(0.82, 186.0, 219.0, 1000, 500000, 20, **MODE_KW["regime"])
+    ref = eng.simulate(prm, seed=2026)
+    for opts in (eng.options(chunk_paths=1 << 20), eng.options(dedup=True), eng.options(int_fast_path=False, chunk_paths=1 << 19)):
+        assert_bitexact(eng.simulate(prm, seed=2026, options=opts)["summary"], ref["summary"], "C4 variant")
+    s = ref["summary"]
+    for g in TIE_GROUPS:
+        for other in g[1:]:
+            assert_bitexact(s[g[0] - 1], s[other - 1], "tie group %s" % (g,))
+    assert (s[:, 5] <= s[:, 6]).all() and (s[:, 6] <= 0).all() and (s[:, 3] <= s[:, 0]).all() and (s[:, 0] <= s[:, 4]).all()
+    assert abs(s[0, 0] - (-19000.0)) < 5 * 3400 / np.sqrt(500000)      # SURVEY A.1 anchor, sd per sim ~3400
+    assert ref["agg"][0].count == 10**7
+
+
+def test_curve_export_matches_reference_equity_curves(eng):
+    """Extension K4: exported curves == np.cumsum of each strategy's contributions on the device-generated
+    sequences (the temporary of :167), bit for bit; layout [20][ceil(L/2)][n][2]."""
+    for name, args, kw in [("dynamic", (0.82, 186.0, 219.0, 1000, 10, 20), {}), ("odd_len", (0.82, 186.0, 219.0, 37, 9, 5), {}),
+                           ("regime", (0.82, 186.0, 219.0, 1000, 6, 4), MODE_KW["regime"]), ("markov2", (0.82, 186.0, 219.0, 129, 7, 4), MODE_KW["markov2"])]:
+        prm = make_params(*args, **kw)
+        P = args[4] * args[5]
+        first, n = 3, P - 5
+        seqs = eng.sequences(prm, seed=8, first_path=first, n=n)
+        L = seqs.shape[1]
+        cur = eng.export_curves(prm, 8, first, n)                      # [20, half, n, 2]
+        got = cur.transpose(0, 2, 1, 3).reshape(20, n, -1)[:, :, :L]   # [20, n, L]
+        assert_bitexact(got, oracle.equity_curves(seqs), name)
+        if L % 2:
+            assert (cur[:, -1, :, 1] == 0).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------

@@ -226,27 +226,59 @@ MCTS_HD void gen_path_codes_fy(const GenSpec &g, uint64_t seed, uint32_t sim, ui
         }
     }
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int w = n_words - 1; w >= 0; w--) {
+    // one swap: position i = 8*w + P (word `cur` in a register), partner j anywhere below
+    auto swap_step = [&](uint32_t &cur, uint32_t w, int P, uint32_t x) {
+        const uint32_t i1 = 8u * w + (uint32_t)P + 1u;
+        const uint32_t j = mulhi32(x, i1);
+        const uint32_t wj = j >> 3, sh = (j << 2) & 28u;
+        uint32_t *slot = codes + (size_t)wj * stride;
+        const uint32_t tj = *slot;
+        const bool alias = wj == w;  // then the live copy is `cur`, the stored one is stale
+        const uint32_t srcw = alias ? cur : tj;
+        const uint32_t d = ((srcw >> sh) ^ (cur >> (4 * P))) & 15u;  // a_i ^ a_j
+        const uint32_t dsh = d << sh;
+        cur = cur ^ (d << (4 * P)) ^ (alias ? dsh : 0u);
+        *slot = tj ^ dsh;  // for an aliased word this is overwritten when `cur` is stored
+    };
+    int w = n_words - 1;
+    if ((L & 7u) != 0u) {  // partial top word: positions >= L do not exist
         uint32_t cur = codes[(size_t)w * stride];
         uint32_t xa[4], xb[4];
         philox4x32_10(k0, k1, 2u * w, k, sim, kStreamShuffle, xa);
         philox4x32_10(k0, k1, 2u * w + 1u, k, sim, kStreamShuffle, xb);
-        const bool full = 8u * (uint32_t)w + 8u <= L;
+        for (int p = (int)(L & 7u) - 1; p >= 0; p--) {
+            uint32_t x = xa[0];
 #pragma unroll
-        for (int p = 7; p >= 0; p--) {
-            const uint32_t i = 8u * (uint32_t)w + (uint32_t)p;
-            if (full || i < L) {
-                const uint32_t j = mulhi32(p < 4 ? xa[p] : xb[p - 4], i + 1u);
-                const uint32_t wj = j >> 3, sh = (j & 7u) << 2;
-                const uint32_t tj = codes[(size_t)wj * stride];
-                const bool alias = wj == (uint32_t)w;  // then the live copy is `cur`, the stored one is stale
-                const uint32_t srcw = alias ? cur : tj;
-                const uint32_t d = ((srcw >> sh) ^ (cur >> (4 * p))) & 15u;  // a_i ^ a_j
-                const uint32_t dsh = d << sh;
-                cur = cur ^ (d << (4 * p)) ^ (alias ? dsh : 0u);
-                codes[(size_t)wj * stride] = tj ^ dsh;  // for an aliased word this is overwritten below
-            }
+            for (int q = 1; q < 8; q++) x = (p == q) ? (q < 4 ? xa[q] : xb[q - 4]) : x;
+            // dynamic nibble position: same swap with run-time shifts
+            const uint32_t i1 = 8u * (uint32_t)w + (uint32_t)p + 1u;
+            const uint32_t j = mulhi32(x, i1);
+            const uint32_t wj = j >> 3, sh = (j << 2) & 28u, shp = 4u * (uint32_t)p;
+            uint32_t *slot = codes + (size_t)wj * stride;
+            const uint32_t tj = *slot;
+            const bool alias = wj == (uint32_t)w;
+            const uint32_t srcw = alias ? cur : tj;
+            const uint32_t d = ((srcw >> sh) ^ (cur >> shp)) & 15u;
+            const uint32_t dsh = d << sh;
+            cur = cur ^ (d << shp) ^ (alias ? dsh : 0u);
+            *slot = tj ^ dsh;
         }
+        codes[(size_t)w * stride] = cur;
+        w--;
+    }
+    for (; w >= 0; w--) {
+        uint32_t cur = codes[(size_t)w * stride];
+        uint32_t xa[4], xb[4];
+        philox4x32_10(k0, k1, 2u * w, k, sim, kStreamShuffle, xa);
+        philox4x32_10(k0, k1, 2u * w + 1u, k, sim, kStreamShuffle, xb);
+        swap_step(cur, (uint32_t)w, 7, xb[3]);
+        swap_step(cur, (uint32_t)w, 6, xb[2]);
+        swap_step(cur, (uint32_t)w, 5, xb[1]);
+        swap_step(cur, (uint32_t)w, 4, xb[0]);
+        swap_step(cur, (uint32_t)w, 3, xa[3]);
+        swap_step(cur, (uint32_t)w, 2, xa[2]);
+        swap_step(cur, (uint32_t)w, 1, xa[1]);
+        swap_step(cur, (uint32_t)w, 0, xa[0]);
         codes[(size_t)w * stride] = cur;
     }
 }

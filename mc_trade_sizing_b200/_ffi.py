@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcts.so")
+LIB_PATH = os.environ.get("MCTS_LIB") or os.path.join(HERE, "libmcts.so")
 
 NSTRAT = 20
 MAX_REGIMES = 16

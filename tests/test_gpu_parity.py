@@ -233,6 +233,27 @@ def test_distribution_agrees_with_reference(eng, stats_golden):
                 assert abs(np.quantile(ref, q) - np.quantile(dev, q)) <= 4.5 * np.std(boots) + 1e-9, (mode, s + 1, q)
 
 
+def test_distribution_agrees_with_seeded_reference_port(eng):
+    """Larger two-sample check: the oracle (bit-exact restatement of the reference incl. MT19937, so its
+    samples ARE reference samples) vs the device RNG, 8000 simulations x 4 shuffles per mode.
+    Tolerances: means within 4.5 clustered standard errors; two-sample Kolmogorov-Smirnov distance of the
+    per-simulation means below the 1e-5 critical value c(alpha)*sqrt(2/n), c = 1.95 * 1.25 safety."""
+    n_sims, n_sh = 8000, 4
+    for mode, kw in MODE_KW.items():
+        args = (0.82, 186.0, 219.0, 1000, n_sims, n_sh)
+        ref = oracle.run_all(oracle.make_params(*args, **kw), 987654, per_path=True)
+        dev = eng.simulate(make_params(*args, **kw), seed=13, per_path=True)
+        for s in range(20):
+            for key in ("profit", "dd"):
+                a, b = ref[key][s], dev[key][s]
+                se = np.hypot(_cluster_se(a, n_sh), _cluster_se(b, n_sh))
+                assert abs(a.mean() - b.mean()) <= 4.5 * se + 1e-9, (mode, s + 1, key, a.mean(), b.mean(), se)
+                ca, cb = np.sort(a.reshape(-1, n_sh).mean(axis=1)), np.sort(b.reshape(-1, n_sh).mean(axis=1))
+                grid = np.concatenate([ca, cb])
+                ks = np.max(np.abs(np.searchsorted(ca, grid, side="right") / ca.size - np.searchsorted(cb, grid, side="right") / cb.size))
+                assert ks <= 1.95 * 1.25 * np.sqrt(2.0 / n_sims), (mode, s + 1, key, ks)
+
+
 def test_analytic_anchor_strategy1(eng):
     """expected profit of strategy 1 from the chains' exact win-count expectations."""
     anchors = {"dynamic": 103063.2, "markov1": 66936.7, "markov2": 57802.5, "regime": -19000.0}

@@ -30,3 +30,16 @@ for r in range(a.reps):
     print("rep %d: %.3f ms total, paths kernel %.3f ms, gen %.3f ms, reduce %.3f ms, %.4g trade-steps/s (kernel %.4g), avg_profit[1]=%.3f"
           % (r, t["total_ms"], t["paths_ms"], t["gen_ms"], t["reduce_ms"], t["trade_steps"] / t["total_ms"] * 1e3,
              t["trade_steps"] / t["paths_ms"] * 1e3, out["summary"][0][0]))
+
+if os.environ.get("MCTS_PROFILE_REPLAY"):
+    import time
+    import numpy as np
+    n = int(os.environ["MCTS_PROFILE_REPLAY"])
+    seqs = eng.sequences(make_params(0.82, 186.0, 219.0, a.trades, n // 20, 20, **kw), seed=1)
+    for r in range(2):
+        t0 = time.perf_counter()
+        eng.replay(seqs, per_path=False)
+        wall = time.perf_counter() - t0
+        t = eng.timing()
+        print("replay %d paths: wall %.1f ms (%.3g trade-steps/s end to end, %.1f MB H2D), kernels %.3f ms (%.3g trade-steps/s)"
+              % (seqs.shape[0], wall * 1e3, t["trade_steps"] / wall, t["h2d_bytes"] / 1e6, t["paths_ms"], t["trade_steps"] / t["paths_ms"] * 1e3))

@@ -46,7 +46,9 @@ typedef enum {
     MCTS_ENOMEM = -3,     /* host or device allocation failed */
     MCTS_ECUDA = -4,      /* CUDA runtime error, message has the details */
     MCTS_ENODEVICE = -5,  /* no usable CUDA device / wrong architecture: there is no CPU fallback */
-    MCTS_EUNSUPPORTED = -6 /* valid for the reference but outside this build's limits (see message) */
+    MCTS_EUNSUPPORTED = -6 /* valid for the reference but outside this build's limits (see message):
+                              > 16 distinct trade values (or > 8 of one sign), > ~14,000 trades per path,
+                              > 16 regimes, non-finite or subnormal trade values in simulate mode */
 } mcts_status;
 
 /* Generator selection, same precedence as trading_models.py:477-490. */
@@ -144,7 +146,8 @@ int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mct
 
 /*
  * Replay: evaluate caller-supplied post-shuffle sequences (replaces :493-507 + :509-518).
- *   values    [P][T] row-major trade results (what np.random.shuffle left in base_results)
+ *   values    [P][T] row-major trade results (what np.random.shuffle left in base_results); any finite
+ *             doubles, including zeros of either sign and the reference's int64 regime arrays
  *   profit,dd optional [20][P]
  */
 int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt,

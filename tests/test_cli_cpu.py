@@ -66,3 +66,24 @@ def test_break_even_helper():
     assert tm.find_break_even_hit_rate(186.0, 219.0, "No Markov") == 219.0 / 405.0
     assert tm.find_break_even_hit_rate(186.0, 219.0, "2nd Order Markov") == 219.0 / 405.0 * (1 + (0.8 - 0.5) / 4)
     assert tm.find_break_even_hit_rate(0, 219.0, "No Markov") is None
+
+
+def test_sweep_builds_the_same_twelve_command_lines_as_dps(monkeypatch):
+    """sweep.sweep_argvs mirrors dps.py:187-191, 211-259 (3 hit rates x 4 modes, str() formatting)."""
+    from mc_trade_sizing_b200 import sweep
+    cfg = {"hit_rate": 0.82, "avg_win": 186, "avg_loss": 219, "num_simulations": 200, "num_trades": 1000, "num_mc_shuffles": 20,
+           "p_win_after_win": 0.8, "p_win_after_loss": 0.4, "p_win_ww": 0.8, "p_win_wl": 0.6, "p_win_lw": 0.5, "p_win_ll": 0.3,
+           "regimes": [{"length": 300, "hit_rate": 0.9, "avg_win": 200, "avg_loss": 100}]}
+    runs = sweep.sweep_argvs(cfg)
+    assert len(runs) == 12
+    assert [r[2][1] for r in runs[::4]] == ["0.72", "0.7699999999999999", "0.82"]          # SURVEY 3.1 [probe]
+    assert runs[1][2][-5:] == ["--use_markov", "--p_win_after_win", "0.8", "--p_win_after_loss", "0.4"]
+    assert runs[3][2][-3:-1] == ["--use_regime", "--regimes"] and json.loads(runs[3][2][-1]) == cfg["regimes"]
+    parser = tm.build_parser()
+    for _, _, argv in runs:
+        parser.parse_args(argv)
+    calls = []
+    monkeypatch.setattr(tm, "run_all_strategies", lambda *a, **k: calls.append((a, k)) or [("x",) + (1.0,) * 9] * 20)
+    out = sweep.run_dps_sweep(cfg)
+    assert len(out) == 12 and len(calls) == 12 and all("Break-even hit rate" in o[3] for o in out)
+    assert calls[3][1]["use_regime"] and calls[3][1]["regimes"] == cfg["regimes"] and calls[2][1]["use_markov2"]

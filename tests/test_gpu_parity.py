@@ -316,6 +316,20 @@ def test_curve_export_matches_reference_equity_curves(eng):
             assert (cur[:, -1, :, 1] == 0).all()
 
 
+def test_curve_parquet_round_trip(eng, tmp_path):
+    import pyarrow.parquet as pq
+    from mc_trade_sizing_b200 import curves
+    prm = make_params(0.82, 186.0, 219.0, 37, 4, 3)
+    fn = str(tmp_path / "curves.parquet")
+    n_rows = curves.write_parquet(eng, prm, 5, 2, 7, fn, strategies=[1, 19])
+    tbl = pq.read_table(fn).to_pandas()
+    assert n_rows == len(tbl) == 2 * 7 * 37
+    ref = oracle.equity_curves(eng.sequences(prm, seed=5, first_path=2, n=7))
+    got = tbl[tbl.strategy_id == 19].sort_values(["path", "trade"]).equity.to_numpy().reshape(7, 37)
+    assert_bitexact(got, ref[18], "parquet curves of strategy 19")
+    assert set(tbl.path) == set(range(2, 9))
+
+
 # ---------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------
@@ -335,6 +349,27 @@ def test_run_all_strategies_drop_in(eng):
     from mc_trade_sizing_b200.trading_models import DESCRIPTIONS
     for i in range(20):
         assert_bitexact(np.array(by_desc[DESCRIPTIONS[i + 1]]), ref[i], "row %d" % (i + 1))
+
+
+def test_dps_sweep_in_one_process(eng):
+    """N2: the 12 runs of dps.py in one process; every block parses with dps.py's row regex (dps.py:356)."""
+    import re
+    from mc_trade_sizing_b200 import sweep
+    cfg = {"hit_rate": 0.82, "avg_win": 186, "avg_loss": 219, "num_simulations": 200, "num_trades": 1000, "num_mc_shuffles": 20,
+           "p_win_after_win": 0.8, "p_win_after_loss": 0.4, "p_win_ww": 0.8, "p_win_wl": 0.6, "p_win_lw": 0.5, "p_win_ll": 0.3,
+           "regimes": README_REGIMES}
+    row = re.compile(r"(.+?)\s+(-?\d+\.\d+)" + r"\s+(-?\d+\.\d+)" * 8)
+    runs = sweep.run_dps_sweep(cfg)
+    assert len(runs) == 12
+    for label, hit_rate, argv, text in runs:
+        rows = [m for m in (row.match(ln) for ln in text.split("\n") if len(ln.split()) >= 10) if m]
+        assert len(rows) == 20, label
+        assert {m.group(1).strip() for m in rows} == set(tm_descriptions())
+
+
+def tm_descriptions():
+    from mc_trade_sizing_b200.trading_models import DESCRIPTIONS
+    return DESCRIPTIONS.values()
 
 
 def test_error_behaviour(eng):

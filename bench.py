@@ -290,6 +290,19 @@ def main():
             t64 = eng.timing()
             extras["other_configs"][name] = {"value": t["trade_steps"] / (t["total_ms"] * 1e-3),
                                              "value_fp64_evaluator": t64["trade_steps"] / (t64["total_ms"] * 1e-3), "unit": UNIT}
+        # (a3) replay mode end to end: caller sequences in (pageable) host memory -> C ABI -> per-strategy aggregates
+        import numpy as np
+        n_rep = 200000
+        seqs = np.ascontiguousarray(eng.sequences(make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, n_rep // NUM_SHUFFLES, NUM_SHUFFLES), seed=5))
+        eng.replay(seqs, per_path=False)
+        t0 = time.perf_counter()
+        eng.replay(seqs, per_path=False)
+        wall = time.perf_counter() - t0
+        t = eng.timing()
+        extras["replay"] = {"e2e_value": t["trade_steps"] / wall, "kernels_value": t["trade_steps"] / (t["paths_ms"] * 1e-3), "unit": UNIT,
+                            "h2d_bytes": int(t["h2d_bytes"]), "d2h_bytes": int(t["d2h_bytes"]), "paths": n_rep,
+                            "note": "replay of caller-supplied fp64 sequences: 8 B per (path, trade) cross PCIe from pageable host memory"}
+        del seqs
         # (b) equity-curve export: HBM-bound, 8 B per trade-step
         n_curve = 1 << 17
         eng.export_curves(small, 3, 0, n_curve, to_host=False)

@@ -138,3 +138,41 @@ def test_int32_evaluator_is_exact_for_integer_runs():
     prm = make_params(0.82, 186.0, 219.0, 100, 3, 2)
     a, b = harness.simulate(prm, 1, int_path=True), harness.simulate(prm, 1)
     assert_bitexact(a["profit"], b["profit"])
+
+
+def test_fuzz_generator_and_evaluator_against_the_oracles():
+    """Random parameter sets (degenerate probabilities, zero / negative / equal / tiny values, random regime
+    lists, all trade counts): device code (host-compiled) == devgen_ref.c sequences == oracle evaluation;
+    errors are raised for exactly the same inputs."""
+    import fuzz_cases
+    ok = err = 0
+    for args, kw in fuzz_cases.random_cases(400, 2026):
+        try:
+            ref_seqs = oracle.devgen_sequences(oracle.make_params(*args, **kw), 4242)
+            ref_err = None
+        except ValueError as e:
+            ref_err = e
+        prm = make_params(*args, **kw)
+        if ref_err is not None or ref_seqs.shape[1] == 0:
+            try:
+                harness.simulate(prm, 4242)
+                raised = False
+            except ValueError:
+                raised = True
+            assert raised, (args, kw)
+            err += 1
+            continue
+        try:
+            out = harness.simulate(prm, 4242, int_path=bool(ok & 1), dedup=bool(ok & 2))
+        except ValueError:
+            # the only inputs the reference accepts but this build rejects: > 8 distinct values of one sign
+            # or values outside [2^-1021, 2^1023]
+            vals = np.unique(ref_seqs)
+            assert (vals > 0).sum() > 8 or (vals <= 0).sum() > 8 or np.any((vals != 0) & (np.abs(vals) < 4.5e-308)), (args, kw)
+            continue
+        assert_bitexact(out["seqs"], ref_seqs, "%s %s" % (args, kw))
+        exp = oracle.eval_paths(ref_seqs)
+        assert_bitexact(out["profit"], exp["profit"], "%s %s profit" % (args, kw))
+        assert_bitexact(out["dd"], exp["dd"], "%s %s dd" % (args, kw))
+        ok += 1
+    assert ok > 250 and err >= 5, (ok, err)

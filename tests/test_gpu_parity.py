@@ -162,6 +162,41 @@ def test_device_generator_matches_independent_restatement(eng):
         assert_bitexact(out["summary"], exp["summary"], name + " summary")
 
 
+def test_fuzz_random_parameter_sets(eng):
+    """400 random parameter sets (degenerate probabilities, zero / negative / equal / tiny values, random
+    regime lists, trade counts 1..1203): GPU sequences == devgen_ref.c, GPU per-path results and
+    aggregates == oracle on those sequences (all evaluator variants), and errors for the same inputs."""
+    import fuzz_cases
+    ok = err = 0
+    for args, kw in fuzz_cases.random_cases(400, 777):
+        prm = make_params(*args, **kw)
+        try:
+            ref_seqs = oracle.devgen_sequences(oracle.make_params(*args, **kw), 99)
+        except ValueError:
+            ref_seqs = None
+        if ref_seqs is None or ref_seqs.shape[1] == 0:
+            with pytest.raises(ValueError):
+                eng.simulate(prm, seed=99)
+            err += 1
+            continue
+        opts = eng.options(dedup=bool(ok & 1), int_fast_path=bool(ok & 2), chunk_paths=128 if ok & 4 else 0)
+        try:
+            out = eng.simulate(prm, seed=99, per_path=True, options=opts)
+        except _ffi.MctsError as e:
+            assert e.code == _ffi.EUNSUPPORTED, (args, kw)
+            vals = np.unique(ref_seqs)
+            assert (vals > 0).sum() > 8 or (vals <= 0).sum() > 8 or np.any((vals != 0) & (np.abs(vals) < 4.5e-308)), (args, kw)
+            continue
+        assert_bitexact(eng.sequences(prm, seed=99), ref_seqs, "%s %s" % (args, kw))
+        exp = oracle.eval_paths(ref_seqs, num_trades=args[3])
+        assert_bitexact(out["profit"], exp["profit"], "%s %s profit" % (args, kw))
+        assert_bitexact(out["dd"], exp["dd"], "%s %s dd" % (args, kw))
+        if args[3] > 0:
+            assert_bitexact(out["summary"], exp["summary"], "%s %s summary" % (args, kw))
+        ok += 1
+    assert ok > 250 and err >= 5, (ok, err)
+
+
 def test_sequences_are_permutations_of_one_multiset_per_simulation(eng):
     prm = make_params(0.82, 186.0, 219.0, 1000, 6, 5)
     seqs = eng.sequences(prm, seed=5)

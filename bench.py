@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, NUM_SHUFFLES = 0.82, 186.0, 219.0, 1000, 20
 SIMS_PER_GPU_STEP = 419432          # x 20 shuffles = 8,388,640 paths = 1.68e11 trade-steps per GPU per step
-CHUNK_PATHS = 1 << 21
+CHUNK_PATHS = 1 << 22          # the library default: two 4.19 M-path chunks per GPU per step, one per stream lane
 METRIC = "trade-steps/sec (paths x trades x strategies)"
 UNIT = "trade-steps/s"
 FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)

@@ -42,6 +42,10 @@ struct PathArgs {
     double *out;              // [40][ld]: row id-1 = profit, row 20+id-1 = drawdown
     int64_t ld;
     double *curves;           // PM_CURVES: [20][ceil(L/2)][n][2]
+    uint32_t *scratch;        // GLOBAL code store (paths too long for shared memory): [word][scratch_stride]
+    int32_t scratch_stride;   // threads in the launch, rounded up to the block size
+    int32_t pad1;
+    int64_t out_off;          // column offset of this launch inside `out` (sub-launches of one chunk)
 };
 
 static __global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__ GenSpec g, uint64_t seed, int64_t sim0, int64_t n_sims, uint32_t *__restrict__ counts)
@@ -101,13 +105,13 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
 #pragma unroll
             for (int other = 1; other <= kNumStrategies; other++) {
                 if (rule_of_id(other) == rule_of_id(id)) {
-                    a.out[(int64_t)(other - 1) * a.ld + local] = profit[s];
-                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + local] = dd[s];
+                    a.out[(int64_t)(other - 1) * a.ld + a.out_off + local] = profit[s];
+                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + a.out_off + local] = dd[s];
                 }
             }
         } else {
-            a.out[(int64_t)(id - 1) * a.ld + local] = profit[s];
-            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + local] = dd[s];
+            a.out[(int64_t)(id - 1) * a.ld + a.out_off + local] = profit[s];
+            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + a.out_off + local] = dd[s];
         }
     });
 }
@@ -118,13 +122,16 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
 // 64-thread blocks and no barriers 47 % of the issue slots were lost to instruction fetch
 // (profiles/r01_ncu_sim_paths_block64_nobarrier.txt).  128 threads (one warp per scheduler, three
 // blocks per SM) measured best; 384 (one block per SM) is 3 % slower.
-template <int K, int MODE, int BLOCK>
+// GLOBAL = true keeps the code columns in global memory ([word][thread], coalesced per word) for
+// paths too long for shared memory; same code otherwise, much slower generation (scattered RMW).
+template <int K, int MODE, int BLOCK, bool GLOBAL = false>
 __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(const __grid_constant__ PathArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     Tab *tab = reinterpret_cast<Tab *>(smem);
-    uint32_t *codes = smem + kTabWords;
     const int tid = threadIdx.x;
+    uint32_t *codes = GLOBAL ? a.scratch + (size_t)blockIdx.x * BLOCK : smem + kTabWords;
+    const int cstride = GLOBAL ? a.scratch_stride : BLOCK;
     for (int i = tid; i < 16 * 4; i += BLOCK) reinterpret_cast<double *>(tab)[i] = reinterpret_cast<const double *>(a.g.tab)[i];
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
@@ -137,14 +144,14 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
         // the code column of a thread is private: the barriers below are for phase alignment only
         if constexpr (K == 2) {
             const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
-            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, BLOCK);
+            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, cstride);
         } else {
-            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
+            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, cstride);
         }
     }
     CodeSource src;
     src.codes = codes + tid;
-    src.stride = BLOCK;
+    src.stride = cstride;
     src.tab = tab;
     src.word = 0;
     if constexpr (MODE == PM_DEDUP) {
@@ -179,13 +186,13 @@ __device__ __forceinline__ void run_pass_int(const uint32_t *codes, int stride, 
 #pragma unroll
             for (int other = 1; other <= kNumStrategies; other++) {
                 if (rule_of_id(other) == rule_of_id(id)) {
-                    a.out[(int64_t)(other - 1) * a.ld + local] = (double)profit[s];
-                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + local] = (double)dd[s];
+                    a.out[(int64_t)(other - 1) * a.ld + a.out_off + local] = (double)profit[s];
+                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + a.out_off + local] = (double)dd[s];
                 }
             }
         } else {
-            a.out[(int64_t)(id - 1) * a.ld + local] = (double)profit[s];
-            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + local] = (double)dd[s];
+            a.out[(int64_t)(id - 1) * a.ld + a.out_off + local] = (double)profit[s];
+            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + a.out_off + local] = (double)dd[s];
         }
     });
 }
@@ -251,12 +258,13 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __gr
     run_pass<IDS, MODE>(src, a, local);
 }
 
-template <int K>
+template <int K, bool GLOBAL = false>
 __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ PathArgs a, double *__restrict__ values)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *codes = smem;
     const int tid = threadIdx.x;
+    uint32_t *codes = GLOBAL ? a.scratch + (size_t)blockIdx.x * kBlock : smem;
+    const int cstride = GLOBAL ? a.scratch_stride : kBlock;
     const int64_t local = (int64_t)blockIdx.x * kBlock + tid;
     if (local >= a.n) return;
     const int64_t path = a.path0 + local;
@@ -265,12 +273,12 @@ __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ Pa
     const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
     if constexpr (K == 2) {
         const uint32_t c2[2] = {cnt[0], cnt[1]};
-        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, kBlock);
+        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, cstride);
     } else {
-        gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, kBlock);
+        gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, cstride);
     }
     for (int t = 0; t < a.g.L; t++) {
-        const uint32_t code = (codes[(t >> 3) * kBlock + tid] >> (4 * (t & 7))) & 15u;
+        const uint32_t code = (codes[(size_t)(t >> 3) * cstride + tid] >> (4 * (t & 7))) & 15u;
         values[local * a.g.L + t] = a.g.tab[code].v1;
     }
 }

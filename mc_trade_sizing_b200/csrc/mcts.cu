@@ -54,6 +54,8 @@ struct mcts_handle {
         int64_t cap_paths = 0;
         double *d_part = nullptr;
         int64_t cap_part = 0;  // 120 * pstride
+        uint32_t *d_scratch = nullptr;  // global code store for very long paths
+        int64_t cap_scratch = 0;
         cudaEvent_t done = nullptr;
     } lane[2];
     cudaStream_t stream = nullptr;  // == lane[0].stream
@@ -203,6 +205,7 @@ void mcts_destroy(mcts_handle *h)
         cudaFree(L.d_counts);
         cudaFree(L.d_out);
         cudaFree(L.d_part);
+        cudaFree(L.d_scratch);
         if (L.done) cudaEventDestroy(L.done);
     }
     cudaFree(h->d_recs);
@@ -364,24 +367,60 @@ static int pick_block(int L, int want)
     return 0;
 }
 
-static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
+// Paths too long for a useful shared-memory residency (fewer than 128 threads per SM, i.e. more than
+// ~3,500 trades) keep their code columns in global memory instead.
+static bool needs_global_codes(int L)
 {
-    const int block = pick_block(a.g.L, h->block_threads);
-    if (!block) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build (limit ~14000 trades)");
-    cudaError_t e;
-    if (h->int_fast_path && a.g.all_int && mode != PM_CURVES) {  // exact int32 evaluator, identical results
-        e = mode == PM_DEDUP ? mcts_launch_paths_int_dedup(a, block, L.stream) : mcts_launch_paths_int_full(a, block, L.stream);
-        if (e != cudaSuccess) return fail(MCTS_ECUDA, std::string("k_sim_paths_int launch failed: ") + cudaGetErrorString(e));
-        h->timing.launches++;
-        return MCTS_OK;
+    int best = 0;
+    for (int b : {128, 64, 32}) {
+        const size_t smem = path_smem_bytes(L, b);
+        if (smem > 227 * 1024) continue;
+        best = std::max(best, std::min(kThreadsPerSM / b, (int)((size_t)228 * 1024 / (smem + 1024))) * b);
     }
-    switch (mode) {
-        case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, L.stream); break;
-        case PM_CURVES: e = mcts_launch_paths_curves(a, block, L.stream); break;
-        default: e = mcts_launch_paths_full(a, block, L.stream); break;
+    return best < 128;
+}
+
+static int launch_one(mcts_handle *h, Lane &L, int mode, const PathArgs &a, int block)
+{
+    cudaError_t e;
+    if (block != 0 && h->int_fast_path && a.g.all_int && mode != PM_CURVES) {  // exact int32 evaluator, identical results
+        e = mode == PM_DEDUP ? mcts_launch_paths_int_dedup(a, block, L.stream) : mcts_launch_paths_int_full(a, block, L.stream);
+    } else {
+        switch (mode) {
+            case PM_DEDUP: e = mcts_launch_paths_dedup(a, block, L.stream); break;
+            case PM_CURVES: e = mcts_launch_paths_curves(a, block, L.stream); break;
+            default: e = mcts_launch_paths_full(a, block, L.stream); break;
+        }
     }
     if (e != cudaSuccess) return fail(MCTS_ECUDA, std::string("k_sim_paths launch failed: ") + cudaGetErrorString(e));
     h->timing.launches++;
+    return MCTS_OK;
+}
+
+static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
+{
+    if (!needs_global_codes(a.g.L)) {
+        const int block = pick_block(a.g.L, h->block_threads);
+        if (!block) return fail(MCTS_EUNSUPPORTED, "internal: no block size fits");
+        return launch_one(h, L, mode, a, block);
+    }
+    if (mode == PM_CURVES) return fail(MCTS_EUNSUPPORTED, "curve export needs paths of at most ~3,500 trades");
+    // global code store: [words][launch threads] u32, at most 1 GiB per launch -> sub-launches of the chunk
+    const int64_t words = (a.g.L + 7) / 8;
+    int64_t sub = (((int64_t)1 << 30) / (words * 4)) / 128 * 128;
+    if (sub < 128) return fail(MCTS_EUNSUPPORTED, "num_trades too large (more than ~16 million trades per path)");
+    sub = std::min<int64_t>(sub, (a.n + 127) / 128 * 128);
+    int rc = ensure(&L.d_scratch, &L.cap_scratch, words * sub);
+    if (rc) return rc;
+    for (int64_t off = 0; off < a.n; off += sub) {
+        PathArgs b = a;
+        b.path0 = a.path0 + off;
+        b.n = std::min<int64_t>(sub, a.n - off);
+        b.out_off = a.out_off + off;
+        b.scratch = L.d_scratch;
+        b.scratch_stride = (int32_t)((b.n + 127) / 128 * 128);
+        if ((rc = launch_one(h, L, mode, b, 0))) return rc;
+    }
     return MCTS_OK;
 }
 
@@ -627,13 +666,25 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
     if (rc) return rc;
     const int L = a.g.L;
     if ((rc = ensure(&h->d_values, &h->cap_values, n * L))) return rc;
-    const size_t smem = (size_t)((L + 7) / 8) * kBlock * 4;
-    if (smem > 227 * 1024) return fail(MCTS_EUNSUPPORTED, "num_trades too large for the shared-memory code store of this build");
+    size_t smem = (size_t)((L + 7) / 8) * kBlock * 4;
+    const bool global = smem > 227 * 1024;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    if (global) {
+        Lane &L0 = h->lane[0];
+        a.scratch_stride = (int32_t)(grid * kBlock);
+        if ((int64_t)((L + 7) / 8) * a.scratch_stride * 4 > ((int64_t)1 << 31)) return fail(MCTS_EUNSUPPORTED, "mcts_sequences: request fewer paths of this length per call");
+        if ((rc = ensure(&L0.d_scratch, &L0.cap_scratch, (int64_t)((L + 7) / 8) * a.scratch_stride))) return rc;
+        a.scratch = L0.d_scratch;
+        smem = 0;
+    }
 #define LAUNCH_SEQ(KK)                                                                                                        \
     do {                                                                                                                      \
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sequences<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-        k_sequences<KK><<<grid, kBlock, smem, h->stream>>>(a, h->d_values);                                                   \
+        if (global) {                                                                                                         \
+            k_sequences<KK, true><<<grid, kBlock, 0, h->stream>>>(a, h->d_values);                                            \
+        } else {                                                                                                              \
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sequences<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            k_sequences<KK, false><<<grid, kBlock, smem, h->stream>>>(a, h->d_values);                                        \
+        }                                                                                                                     \
     } while (0)
     if (a.g.K <= 2) LAUNCH_SEQ(2);
     else LAUNCH_SEQ(16);

@@ -31,9 +31,19 @@ static cudaError_t launch_k(const PathArgs &a, int block, cudaStream_t stream)
     return cudaErrorInvalidValue;
 }
 
+template <int K, int MODE>
+static cudaError_t launch_global(const PathArgs &a, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)((a.n + 127) / 128);
+    k_sim_paths<K, MODE, 128, true><<<grid, 128, (size_t)kTabWords * 4, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// block == 0: code columns in global memory (a.scratch)
 template <int MODE>
 static cudaError_t launch_mode(const PathArgs &a, int block, cudaStream_t stream)
 {
+    if (block == 0) return a.g.K <= 2 ? launch_global<2, MODE>(a, stream) : launch_global<16, MODE>(a, stream);
     if (a.g.K <= 2) return launch_k<2, MODE>(a, block, stream);  // two values: register urn
     return launch_k<16, MODE>(a, block, stream);                // up to 16 values: Fisher-Yates in shared memory
 }

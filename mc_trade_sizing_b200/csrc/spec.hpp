@@ -20,7 +20,7 @@ constexpr int kNumStrategies = 20;
 constexpr int kMaxCat = 16;       // distinct trade values per run (4-bit codes: <= 8 positive and <= 8 non-positive)
 constexpr int kMaxSeg = 20;       // 16 regimes, or the 3 phases + tail fill of :44-65
 constexpr int kMaxStackDepth = 12; // pairwise-tree depth over trades: T <= 128 * 2^11
-constexpr int kMaxLeaves = 512;
+constexpr int kMaxLeaves = 4096;  // <= ~260,000 trades per path
 
 struct Segment {  // one np.random.choice([win, -loss], size=len, p=[p, 1-p]) block (:55-59, :119-123)
     int32_t len;

@@ -197,6 +197,23 @@ def test_fuzz_random_parameter_sets(eng):
     assert ok > 250 and err >= 5, (ok, err)
 
 
+def test_long_paths_use_the_global_code_store(eng):
+    """Paths too long for shared-memory code columns (> ~3,500 trades) keep them in global memory: same
+    generator specification, same evaluator, same results."""
+    for T, ns, nsh, kw in ((3000, 6, 4, {}), (5000, 5, 3, {}), (20001, 3, 2, MODE_KW["markov1"]), (40000, 2, 2, {}),
+                           (7000, 4, 3, dict(use_regime=True, regimes=None))):
+        args = (0.82, 186.0, 219.0, T, ns, nsh)
+        prm = make_params(*args, **kw)
+        ref_seqs = oracle.devgen_sequences(oracle.make_params(*args, **kw), 2718)
+        assert_bitexact(eng.sequences(prm, seed=2718), ref_seqs, "T=%d sequences" % T)
+        exp = oracle.eval_paths(ref_seqs, num_trades=T)
+        for opts in (eng.options(), eng.options(dedup=True, int_fast_path=False)):
+            out = eng.simulate(prm, seed=2718, per_path=True, options=opts)
+            assert_bitexact(out["profit"], exp["profit"], "T=%d profit" % T)
+            assert_bitexact(out["dd"], exp["dd"], "T=%d dd" % T)
+            assert_bitexact(out["summary"], exp["summary"], "T=%d summary" % T)
+
+
 def test_sequences_are_permutations_of_one_multiset_per_simulation(eng):
     prm = make_params(0.82, 186.0, 219.0, 1000, 6, 5)
     seqs = eng.sequences(prm, seed=5)

@@ -335,9 +335,9 @@ def main():
     roofline = {
         "bound": "fp64-issue", "kernel": "k_sim_paths", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / peak_tflops,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one k_sim_paths launch of this workload (1,048,580 paths), from the
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_sim_paths launch of this workload (2,097,160 paths), from the
         # committed `ncu --set full` capture profiles/r01_ncu_bench_sim_paths.txt; algorithmic bytes per launch = paths x 320 B
-        "traffic": 295.8e6, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 1048580 * 320,
+        "traffic": 636.6e6, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
         "bound_note": "neither HBM (0.016 B per trade-step) nor tensor cores (no contraction) bound this kernel; SURVEY 8(d) "
                       "prescribes the SM issue / FP64-pipe roofline used here; the HBM roofline of curve-export mode is under curve_export",
         "definition": "achieved = 6 algorithmic fp64 ops per trade-step (SURVEY 8d) x trade-steps per launch / mean launch "

@@ -306,33 +306,51 @@ static __global__ void __launch_bounds__(128) k_reduce_nodes(const double *__res
     part[(int64_t)(80 + arr) * pstride + j] = mx;
 }
 
-// one block of 64 threads, thread arr < 40 folds the 2^d partials of its array pairwise
-static __global__ void __launch_bounds__(64) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
+// grid 40 (one block per array): fold the 2^d node sums pairwise (the perfect-binary top of the
+// tree), level by level, ping-ponging between `part` row `arr` and scratch row 120 + arr; min / max
+// by block reduction.  The additions are exactly those of the sequential fold, only run in parallel.
+static __global__ void __launch_bounds__(256) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
 {
-    const int arr = threadIdx.x;
-    if (arr >= 40) return;
-    double *p = part + (int64_t)arr * pstride;
+    const int arr = blockIdx.x, tid = threadIdx.x;
+    double *p = part + (int64_t)arr * pstride, *q = part + (int64_t)(120 + arr) * pstride;
     const int64_t w0 = (int64_t)1 << d;
-    for (int64_t w = w0; w > 1; w >>= 1)
-        for (int64_t i = 0; i < (w >> 1); i++) p[i] = p[2 * i] + p[2 * i + 1];
+    for (int64_t w = w0; w > 1; w >>= 1) {
+        for (int64_t i = tid; i < (w >> 1); i += 256) q[i] = p[2 * i] + p[2 * i + 1];
+        __syncthreads();
+        double *t = p;
+        p = q;
+        q = t;
+    }
     const double *pmn = part + (int64_t)(40 + arr) * pstride, *pmx = part + (int64_t)(80 + arr) * pstride;
     double mn = pmn[0], mx = pmx[0];
-    for (int64_t i = 1; i < w0; i++) {
+    for (int64_t i = tid; i < w0; i += 256) {
         mn = pmn[i] < mn ? pmn[i] : mn;
         mx = pmx[i] > mx ? pmx[i] : mx;
     }
+    __shared__ double smn[256], smx[256];
+    smn[tid] = mn;
+    smx[tid] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) {
+            smn[tid] = smn[tid + s] < smn[tid] ? smn[tid + s] : smn[tid];
+            smx[tid] = smx[tid + s] > smx[tid] ? smx[tid + s] : smx[tid];
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
     if (arr == 0) {
         rec->first_path = first_path;
         rec->n_paths = n;
     }
     if (arr < 20) {
         rec->sum_profit[arr] = p[0];
-        rec->min_profit[arr] = mn;
-        rec->max_profit[arr] = mx;
+        rec->min_profit[arr] = smn[0];
+        rec->max_profit[arr] = smx[0];
     } else {
         rec->sum_dd[arr - 20] = p[0];
-        rec->min_dd[arr - 20] = mn;
-        rec->max_dd[arr - 20] = mx;
+        rec->min_dd[arr - 20] = smn[0];
+        rec->max_dd[arr - 20] = smx[0];
     }
 }
 

@@ -53,7 +53,7 @@ struct mcts_handle {
         double *d_out = nullptr;
         int64_t cap_paths = 0;
         double *d_part = nullptr;
-        int64_t cap_part = 0;  // 120 * pstride
+        int64_t cap_part = 0;  // 160 * pstride
         uint32_t *d_scratch = nullptr;  // global code store for very long paths
         int64_t cap_scratch = 0;
         cudaEvent_t done = nullptr;
@@ -440,14 +440,14 @@ static int launch_reduce(mcts_handle *h, Lane &L, int64_t n, int64_t first_path,
 {
     const int d = reduce_depth(n);
     const int64_t nodes = (int64_t)1 << d;
-    int rc = ensure(&L.d_part, &L.cap_part, std::max<int64_t>(nodes, 1024) * 120);
+    int rc = ensure(&L.d_part, &L.cap_part, std::max<int64_t>(nodes, 1024) * 160);  // 120 rows + 40 ping-pong rows
     if (rc) return rc;
-    const int64_t pstride = L.cap_part / 120;
+    const int64_t pstride = L.cap_part / 160;
     if ((rc = mark(h, L.stream, h->ev_reduce, true))) return rc;
     dim3 grid((unsigned)((nodes + 127) / 128), 40);
     k_reduce_nodes<<<grid, 128, 0, L.stream>>>(L.d_out, L.cap_paths, n, d, L.d_part, pstride);
     CUDA_TRY(cudaGetLastError());
-    k_reduce_top<<<1, 64, 0, L.stream>>>(L.d_part, pstride, d, d_rec, first_path, n);
+    k_reduce_top<<<40, 256, 0, L.stream>>>(L.d_part, pstride, d, d_rec, first_path, n);
     CUDA_TRY(cudaGetLastError());
     h->timing.launches += 2;
     return mark(h, L.stream, h->ev_reduce, false);

@@ -160,15 +160,16 @@ class Engine:
         return agg
 
     # -- equity-curve export (extension) ------------------------------------------------------
-    def export_curves(self, params: Params, seed: int, first_path: int, n: int, to_host: bool = True):
+    def export_curves(self, params: Params, seed: int, first_path: int, n: int, to_host: bool = True, dev=None):
         """Equity curves [20, ceil(L/2), n, 2] of paths [first_path, first_path+n).  With to_host=False
-        only the device write is performed (bandwidth measurement) and None is returned."""
+        only the device write is performed (bandwidth measurement / streaming) and None is returned.
+        `dev` is an optional device buffer from device_alloc() that is reused instead of a fresh one."""
         L = int(lib().mcts_sequence_length(C.byref(params)))
         half = (L + 1) // 2
         nbytes = NSTRAT * half * n * 2 * 8
-        dev = lib().mcts_device_alloc(self._h, nbytes)
-        if not dev:
-            _raise(_ffi.ENOMEM)
+        own = dev is None
+        if own:
+            dev = self.device_alloc(nbytes)
         try:
             _raise(lib().mcts_export_curves(self._h, C.byref(params), C.c_uint64(seed & (2**64 - 1)), int(first_path), int(n), dev))
             if not to_host:
@@ -177,7 +178,17 @@ class Engine:
             _raise(lib().mcts_copy_to_host(self._h, out.ctypes.data_as(C.c_void_p), dev, nbytes))
             return out
         finally:
-            lib().mcts_device_free(self._h, dev)
+            if own:
+                self.device_free(dev)
+
+    def device_alloc(self, nbytes: int):
+        dev = lib().mcts_device_alloc(self._h, int(nbytes))
+        if not dev:
+            _raise(_ffi.ENOMEM)
+        return dev
+
+    def device_free(self, dev):
+        lib().mcts_device_free(self._h, dev)
 
     # -- measurement ----------------------------------------------------------------------------
     def timing(self) -> dict:

@@ -1,16 +1,19 @@
 // kernels.cuh -- the sm_100a kernels of the path-simulation core.
 //
-//   k_gen_base      one thread per simulation: category counts of the base sequence (generators
-//                   src/trading_models.py:43-128 on Philox uniforms)
-//   k_sim_paths     THE hot kernel, one thread per path (= simulation x shuffle, :491-507):
-//                   shuffle the simulation's outcome multiset (Fisher-Yates; urn for 2 values) into a thread-private shared-memory
-//                   column (4 bits per trade), then evaluate the 20 strategies in passes of five with
-//                   equity/peak/drawdown/profit accumulators in fp64 registers; per-path results
-//                   go to HBM once (320 B per path = 0.016 B per trade-step)
-//   k_replay_pass   same evaluator on caller-supplied fp64 sequences (replay mode)
-//   k_reduce_*      np.mean-ordered (pairwise) sums + min/max over the paths of a chunk (:513-518)
-//   k_sequences     audit hook: the generated sequences as doubles
-//   k_peak_*        issue-rate microbenchmarks (roofline denominators)
+//   k_gen_base        one thread per simulation: per-value counts of the base sequence (generators
+//                     src/trading_models.py:43-128 on Philox uniforms)
+//   k_sim_paths       THE hot kernel, one thread per path (= simulation x shuffle, :491-507):
+//                     shuffle the simulation's outcome multiset (Fisher-Yates; urn for 2 values) into a
+//                     thread-private code column (4 bits per trade; shared memory, or global memory for
+//                     paths longer than ~3,500 trades), then evaluate the 20 strategies in passes of
+//                     five with equity / peak / drawdown / profit accumulators in fp64 registers;
+//                     per-path results go to HBM once (320 B per path = 0.016 B per trade-step).
+//                     MODE: all 20 ids, the 11 distinct behaviours (dedup), or all 20 + equity curves
+//   k_sim_paths_int   the same with the exact int32 evaluator (all-integer runs)
+//   k_replay_pass     the fp64 evaluator on caller-supplied sequences (replay mode), one pass per launch
+//   k_reduce_nodes/top  np.mean-ordered (pairwise) sums + min/max over the paths of a chunk (:513-518)
+//   k_sequences       audit hook: the generated sequences as doubles
+//   k_peak_dadd/int   issue-rate microbenchmarks (roofline denominators)
 #pragma once
 #include <cuda_runtime.h>
 

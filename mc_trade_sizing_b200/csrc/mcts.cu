@@ -174,7 +174,7 @@ int mcts_create(int device, mcts_handle **out)
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
-        char buf[256];
+        char buf[512];
         snprintf(buf, sizeof buf, "device %d (%s) is compute capability %d.%d; libmcts is built for sm_100a only", device, prop.name, prop.major, prop.minor);
         return fail(MCTS_ENODEVICE, buf);
     }

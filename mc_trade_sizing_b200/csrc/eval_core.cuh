@@ -19,6 +19,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
 #include <utility>
 
 #include "spec.hpp"
@@ -61,8 +62,8 @@ struct IdList {
 // id carries its own equity / peak / drawdown / profit chain
 using FullPass0 = IdList<1, 2, 4, 6, 9>;
 using FullPass1 = IdList<3, 13, 5, 7, 10>;
-using FullPass2 = IdList<14, 15, 11, 8, 16>;
-using FullPass3 = IdList<17, 12, 18, 19, 20>;
+using FullPass2 = IdList<14, 15, 16, 11, 18>;
+using FullPass3 = IdList<17, 12, 19, 20, 8>;
 // one representative per behaviour class (results fanned out by the caller)
 using DedupPass0 = IdList<1, 2, 4, 6>;
 using DedupPass1 = IdList<8, 9, 11, 16>;
@@ -111,6 +112,40 @@ MCTS_HD Masks make_masks(uint32_t W, uint32_t Lb, History &h)
 }
 MCTS_HD constexpr uint32_t mask_bit(int i) { return 2u << (4 * i); }
 
+// From the second block on every trade has two real predecessors, so "lost" is simply "did not win":
+// one history word, pl = ~pw, s16 = pll, and the pl-rules reuse the pw predicate negated.
+MCTS_HD Masks make_masks_binary(uint32_t W, History &h)
+{
+    Masks m;
+    const uint32_t pw = (W << 5) | (h.w >> 27), ppw = (W << 9) | (h.w >> 23);
+    m.pw = pw;
+    m.pl = ~pw;
+    m.pww = pw & ppw;
+    m.pll = ~(pw | ppw);
+    m.fw = pw & ~ppw;
+    m.s16 = m.pll;
+    h.w = W;
+    h.l = W ^ 0x11111111u;
+    return m;
+}
+
+// the predicates of one trade (unused ones are dead code)
+struct Preds {
+    bool pw, pl, pww, pll, fw, s16;
+};
+template <bool BINARY>
+MCTS_HD Preds trade_preds(const Masks &m, uint32_t bit)
+{
+    Preds p;
+    p.pw = (m.pw & bit) != 0;
+    p.pww = (m.pww & bit) != 0;
+    p.pll = (m.pll & bit) != 0;
+    p.fw = (m.fw & bit) != 0;
+    p.pl = BINARY ? !p.pw : (m.pl & bit) != 0;
+    p.s16 = BINARY ? p.pll : (m.s16 & bit) != 0;
+    return p;
+}
+
 // p ? v2 : v1 where v2 == 2*v1.  SHARED_LO: the caller guarantees that v1 is zero or a normal number
 // whose double is finite (checked on the host for the categorical path), so v2 and v1 have the same
 // low word and only the high word needs a select -- one ALU instruction instead of two.
@@ -125,19 +160,19 @@ MCTS_HD double select_double_or_single(bool p, double v2, double v1)
 
 // contribution of the current trade for one behaviour: a select among {0, v, 2v, fl(3v)}
 template <int RULE, bool SHARED_LO>
-MCTS_HD double contribution(const Masks &m, uint32_t bit, double v1, double v2, double v3)
+MCTS_HD double contribution(const Preds &p, double v1, double v2, double v3)
 {
     if constexpr (RULE == R_C1) return v1;
-    if constexpr (RULE == R_AM) return select_double_or_single<SHARED_LO>((m.pw & bit) != 0, v2, v1);
-    if constexpr (RULE == R_F1) return select_double_or_single<SHARED_LO>((m.fw & bit) != 0, v2, v1);
-    if constexpr (RULE == R_MG) return select_double_or_single<SHARED_LO>((m.pl & bit) != 0, v2, v1);
-    if constexpr (RULE == R_MG2) return select_double_or_single<SHARED_LO>((m.pll & bit) != 0, v2, v1);
-    if constexpr (RULE == R_P1) return (m.pw & bit) ? 0.0 : v1;
-    if constexpr (RULE == R_P2) return (m.pww & bit) ? 0.0 : v1;
-    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0.0 : select_double_or_single<SHARED_LO>((m.s16 & bit) != 0, v2, v1);
-    if constexpr (RULE == R_S18) return (m.pww & bit) ? v3 : v1;
-    if constexpr (RULE == R_S19) return (m.pll & bit) ? v3 : select_double_or_single<SHARED_LO>((m.pww & bit) != 0, v2, v1);
-    if constexpr (RULE == R_S20) return (m.pll & bit) ? v3 : v1;
+    if constexpr (RULE == R_AM) return select_double_or_single<SHARED_LO>(p.pw, v2, v1);
+    if constexpr (RULE == R_F1) return select_double_or_single<SHARED_LO>(p.fw, v2, v1);
+    if constexpr (RULE == R_MG) return select_double_or_single<SHARED_LO>(p.pl, v2, v1);
+    if constexpr (RULE == R_MG2) return select_double_or_single<SHARED_LO>(p.pll, v2, v1);
+    if constexpr (RULE == R_P1) return p.pw ? 0.0 : v1;
+    if constexpr (RULE == R_P2) return p.pww ? 0.0 : v1;
+    if constexpr (RULE == R_S16) return p.pw ? 0.0 : select_double_or_single<SHARED_LO>(p.s16, v2, v1);
+    if constexpr (RULE == R_S18) return p.pww ? v3 : v1;
+    if constexpr (RULE == R_S19) return p.pll ? v3 : select_double_or_single<SHARED_LO>(p.pww, v2, v1);
+    if constexpr (RULE == R_S20) return p.pll ? v3 : v1;
     return v1;
 }
 
@@ -197,19 +232,19 @@ struct NoSink {
     }
 };
 
-template <class IDS, class SRC, class SINK>
+template <class IDS, bool BINARY, class SRC, class SINK>
 MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t0)
 {
-    const Masks m = make_masks(W, W ^ 0x11111111u, a.h);
+    const Masks m = BINARY ? make_masks_binary(W, a.h) : make_masks(W, W ^ 0x11111111u, a.h);
     static_for<8>([&](auto I) {
         constexpr int i = decltype(I)::value;
         double v1, v2, v3;
         src.template get<i>(v1, v2, v3);
-        constexpr uint32_t bit = mask_bit(i);
+        const Preds p = trade_preds<BINARY>(m, mask_bit(i));
         static_for<IDS::N>([&](auto S) {
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
-            const double c = contribution<rule, SRC::kSharedLo>(m, bit, v1, v2, v3);
+            const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
             trade_step(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
@@ -225,11 +260,11 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
     for (int i = 0; i < count; i++) {
         double v1, v2, v3;
         src.get_dyn(i, v1, v2, v3);
-        const uint32_t bit = mask_bit(i);
+        const Preds p = trade_preds<false>(m, mask_bit(i));
         static_for<IDS::N>([&](auto S) {
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
-            const double c = contribution<rule, SRC::kSharedLo>(m, bit, v1, v2, v3);
+            const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
             trade_step(a.E[s], a.peak[s], a.dd[s], res[s], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
@@ -249,14 +284,20 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
     double stk[NS][kMaxStackDepth];
     double res[NS];
     int sp = 0;
-    int oct = 0;
+    int oct = 0, leaf_start = 0;
     const int n_leaves = sch->n_leaves;
+    if (sch->n_oct > 0) {  // first block: three-valued history ("nothing before the first trade")
+        const uint32_t W = src.load(0);
+        eval_block8<IDS, false>(a, W, src, sink, 0);
+        oct = 1;
+    }
     for (int leaf = 0; leaf < n_leaves; leaf++) {
         const int end = sch->end_oct[leaf];
-        const bool has_blocks = oct < end;
+        const bool has_blocks = leaf_start < end;
+        leaf_start = end;
         for (; oct < end; oct++) {
             const uint32_t W = src.load(oct);
-            eval_block8<IDS>(a, W, src, sink, oct * 8);
+            eval_block8<IDS, true>(a, W, src, sink, oct * 8);
         }
 #pragma unroll
         for (int s = 0; s < NS; s++) {
@@ -298,19 +339,19 @@ struct IntTab {
 };
 
 template <int RULE>
-MCTS_HD int32_t contribution_i(const Masks &m, uint32_t bit, int32_t v1, int32_t v2, int32_t v3)
+MCTS_HD int32_t contribution_i(const Preds &p, int32_t v1, int32_t v2, int32_t v3)
 {
     if constexpr (RULE == R_C1) return v1;
-    if constexpr (RULE == R_AM) return (m.pw & bit) ? v2 : v1;
-    if constexpr (RULE == R_F1) return (m.fw & bit) ? v2 : v1;
-    if constexpr (RULE == R_MG) return (m.pl & bit) ? v2 : v1;
-    if constexpr (RULE == R_MG2) return (m.pll & bit) ? v2 : v1;
-    if constexpr (RULE == R_P1) return (m.pw & bit) ? 0 : v1;
-    if constexpr (RULE == R_P2) return (m.pww & bit) ? 0 : v1;
-    if constexpr (RULE == R_S16) return (m.pw & bit) ? 0 : ((m.s16 & bit) ? v2 : v1);
-    if constexpr (RULE == R_S18) return (m.pww & bit) ? v3 : v1;
-    if constexpr (RULE == R_S19) return (m.pll & bit) ? v3 : ((m.pww & bit) ? v2 : v1);
-    if constexpr (RULE == R_S20) return (m.pll & bit) ? v3 : v1;
+    if constexpr (RULE == R_AM) return p.pw ? v2 : v1;
+    if constexpr (RULE == R_F1) return p.fw ? v2 : v1;
+    if constexpr (RULE == R_MG) return p.pl ? v2 : v1;
+    if constexpr (RULE == R_MG2) return p.pll ? v2 : v1;
+    if constexpr (RULE == R_P1) return p.pw ? 0 : v1;
+    if constexpr (RULE == R_P2) return p.pww ? 0 : v1;
+    if constexpr (RULE == R_S16) return p.pw ? 0 : (p.s16 ? v2 : v1);
+    if constexpr (RULE == R_S18) return p.pww ? v3 : v1;
+    if constexpr (RULE == R_S19) return p.pll ? v3 : (p.pww ? v2 : v1);
+    if constexpr (RULE == R_S20) return p.pll ? v3 : v1;
     return v1;
 }
 
@@ -332,23 +373,26 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
     h.w = 0;
     h.l = 0;
     const int n_oct = L >> 3, tail = L & 7;
-    for (int oct = 0; oct < n_oct; oct++) {
+    auto block = [&](int oct, auto B) {
+        constexpr bool BINARY = decltype(B)::value;
         const uint32_t word = codes[(size_t)oct * stride];
         const uint32_t W = word & 0x11111111u;
-        const Masks m = make_masks(W, W ^ 0x11111111u, h);
+        const Masks m = BINARY ? make_masks_binary(W, h) : make_masks(W, W ^ 0x11111111u, h);
         static_for<8>([&](auto I) {
             constexpr int i = decltype(I)::value;
             const IntTab t = tab[(word >> (4 * i)) & 15u];
-            constexpr uint32_t bit = mask_bit(i);
+            const Preds p = trade_preds<BINARY>(m, mask_bit(i));
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                E[s] += contribution_i<rule>(m, bit, t.v1, t.v2, t.v3);
+                E[s] += contribution_i<rule>(p, t.v1, t.v2, t.v3);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });
         });
-    }
+    };
+    if (n_oct > 0) block(0, std::false_type{});
+    for (int oct = 1; oct < n_oct; oct++) block(oct, std::true_type{});
     if (tail) {
         const uint32_t word = codes[(size_t)n_oct * stride];
         const uint32_t valid = 0x11111111u & ((1u << (4 * tail)) - 1u);
@@ -356,11 +400,11 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
         const Masks m = make_masks(W, W ^ valid, h);
         for (int i = 0; i < tail; i++) {
             const IntTab t = tab[(word >> (4 * i)) & 15u];
-            const uint32_t bit = mask_bit(i);
+            const Preds p = trade_preds<false>(m, mask_bit(i));
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                E[s] += contribution_i<rule>(m, bit, t.v1, t.v2, t.v3);
+                E[s] += contribution_i<rule>(p, t.v1, t.v2, t.v3);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });

@@ -348,6 +348,9 @@ def main():
         "kernel_share_of_step": kstat["paths_ms"] / max(kstat["total_ms"], 1e-9),
         "int_alu_inst_per_s": peaks["int_inst_per_s"], "fp64_inst_per_s": peaks["fp64_inst_per_s"],
         "sm_clock_mhz_microbench": peaks["sm_clock_mhz"],
+        # what the evaluator's instruction mix can reach on this chip: register-only replica of the trade step at the same
+        # occupancy (mcts_measure_step_ceiling): DSETP and the ALU-pipe selects do not overlap, so the step costs ~16 cycles
+        "mix_ceiling": {"strategy_steps_per_s": peaks["step_ceiling_per_s"], "kernel_frac": kernel_rate / peaks["step_ceiling_per_s"]},
         "hbm_note": "aggregate mode moves 0.016 B per trade-step (per-path results only); HBM bounds only curve export",
     }
 

@@ -197,6 +197,9 @@ void *mcts_get_stream(const mcts_handle *h);
  * and independent IADD3/LOP3 chains over the whole chip. Results in warp-wide... thread-level
  * instructions per second. */
 int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst_per_s, double *sm_clock_mhz);
+/* Rate (strategy-steps/s) of a register-only replica of the evaluator's trade step at the hot kernel's
+ * occupancy: the ceiling of this instruction mix on the chip (no generator, no memory). */
+int mcts_measure_step_ceiling(mcts_handle *h, double *strategy_steps_per_s);
 
 #ifdef __cplusplus
 }

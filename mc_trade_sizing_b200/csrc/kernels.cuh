@@ -404,4 +404,44 @@ static __global__ void __launch_bounds__(256) k_peak_int(unsigned *out, int iter
     if (s == 0x12345u) out[0] = s;
 }
 
+// Register-only replica of the evaluator's trade step (3 DADD + 2 DSETP + 5 FSEL + 1 predicate test per
+// strategy-step; five strategies per thread, 128-thread blocks, three blocks per SM like k_sim_paths):
+// the rate this instruction mix can reach on the chip with no generator, no shared memory and no
+// stores.  Measured: ~2.3e12 strategy-steps/s at any occupancy from 8 to 64 warps per SM -- DSETP and
+// the ALU selects do not overlap (tools/mix_bench.cu).
+static __global__ void __launch_bounds__(128, 3) k_peak_step(double *out, int steps8, double v1, double v2, unsigned seed)
+{
+    constexpr int NS = 5;
+    double E[NS], peak[NS], dd[NS], r[NS][8];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        E[s] = -0.0;
+        peak[s] = -1e300;
+        dd[s] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[s][j] = -0.0;
+    }
+    unsigned w = seed * 2654435761u + threadIdx.x * 40503u + blockIdx.x;
+    for (int it = 0; it < steps8; it++) {
+        w = w * 1664525u + 1013904223u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const bool p = (w >> (4 * i + (s & 3))) & 1u;
+                const double c = __hiloint2double(p ? __double2hiint(v2) : __double2hiint(v1), __double2loint(v1));
+                trade_step(E[s], peak[s], dd[s], r[s][i], (s & 1) ? c : -c);
+            }
+        }
+    }
+    double acc = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        acc += E[s] + peak[s] + dd[s];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += r[s][j];
+    }
+    if (steps8 < 0) out[0] = acc;
+}
+
 }  // namespace mcts

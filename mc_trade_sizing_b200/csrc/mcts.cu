@@ -745,6 +745,31 @@ int mcts_copy_to_host(mcts_handle *h, void *dst_host, const void *src_dev, int64
     return MCTS_OK;
 }
 
+int mcts_measure_step_ceiling(mcts_handle *h, double *strategy_steps_per_s)
+{
+    if (!h || !strategy_steps_per_s) return fail(MCTS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 3 * 4, steps8 = 2000;
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 64));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    float ms = 0;
+    for (int rep = 0; rep < 3; rep++) {  // last repetition counts
+        CUDA_TRY(cudaEventRecord(a, h->stream));
+        k_peak_step<<<blocks, 128, 0, h->stream>>>(d_out, steps8, 186.0, 372.0, (unsigned)rep);
+        CUDA_TRY(cudaEventRecord(b, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    }
+    *strategy_steps_per_s = (double)blocks * 128 * steps8 * 8 * 5 / (ms * 1e-3);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    return MCTS_OK;
+}
+
 int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst_per_s, double *sm_clock_mhz)
 {
     if (!h) return fail(MCTS_EINVAL, "NULL handle");

@@ -203,4 +203,6 @@ class Engine:
     def measure_peaks(self) -> dict:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _raise(lib().mcts_measure_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"fp64_inst_per_s": a.value, "int_inst_per_s": b.value, "sm_clock_mhz": c.value}
+        d = C.c_double()
+        _raise(lib().mcts_measure_step_ceiling(self._h, C.byref(d)))
+        return {"fp64_inst_per_s": a.value, "int_inst_per_s": b.value, "sm_clock_mhz": c.value, "step_ceiling_per_s": d.value}

@@ -119,6 +119,22 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
     });
 }
 
+// Phase 0 of the path kernels: shuffle the multiset of this thread's simulation into its code column.
+template <int K>
+__device__ __forceinline__ void generate_codes(const PathArgs &a, int64_t local, uint32_t *column, int stride)
+{
+    const int64_t path = a.path0 + local;
+    const int64_t sim = path / a.n_sh;
+    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+    const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
+    if constexpr (K == 2) {  // two distinct values: register urn
+        const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
+        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, column, stride);
+    } else {  // up to 16 values: Fisher-Yates on the packed column
+        gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, column, stride);
+    }
+}
+
 // BLOCK threads per block, 384 threads per SM.  The threads of a block do not exchange data; the
 // barriers between phases only keep the warps of a block inside the same ~8 KB loop body so that the
 // instruction caches see few bodies at a time: the kernel is ~100 KB of unrolled code, and with
@@ -139,19 +155,8 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
     const bool active = local < a.n;
-    if (active) {
-        const int64_t path = a.path0 + local;
-        const int64_t sim = path / a.n_sh;
-        const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-        const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
-        // the code column of a thread is private: the barriers below are for phase alignment only
-        if constexpr (K == 2) {
-            const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
-            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, cstride);
-        } else {
-            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, cstride);
-        }
-    }
+    // the code column of a thread is private: the barriers below are for phase alignment only
+    if (active) generate_codes<K>(a, local, codes + tid, cstride);
     CodeSource src;
     src.codes = codes + tid;
     src.stride = cstride;
@@ -219,18 +224,7 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
     const bool active = local < a.n;
-    if (active) {
-        const int64_t path = a.path0 + local;
-        const int64_t sim = path / a.n_sh;
-        const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-        const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
-        if constexpr (K == 2) {
-            const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
-            gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, BLOCK);
-        } else {
-            gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, BLOCK);
-        }
-    }
+    if (active) generate_codes<K>(a, local, codes + tid, BLOCK);
     if constexpr (MODE == PM_DEDUP) {
         __syncthreads();
         if (active) run_pass_int<DedupPass0, MODE>(codes + tid, BLOCK, tab, a, local);
@@ -270,16 +264,7 @@ __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ Pa
     const int cstride = GLOBAL ? a.scratch_stride : kBlock;
     const int64_t local = (int64_t)blockIdx.x * kBlock + tid;
     if (local >= a.n) return;
-    const int64_t path = a.path0 + local;
-    const int64_t sim = path / a.n_sh;
-    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
-    const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
-    if constexpr (K == 2) {
-        const uint32_t c2[2] = {cnt[0], cnt[1]};
-        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, codes + tid, cstride);
-    } else {
-        gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, codes + tid, cstride);
-    }
+    generate_codes<K>(a, local, codes + tid, cstride);
     for (int t = 0; t < a.g.L; t++) {
         const uint32_t code = (codes[(size_t)(t >> 3) * cstride + tid] >> (4 * (t & 7))) & 15u;
         values[local * a.g.L + t] = a.g.tab[code].v1;

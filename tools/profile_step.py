@@ -14,6 +14,7 @@ ap.add_argument("--mode", default="dynamic")
 ap.add_argument("--sims", type=int, default=104857)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--trades", type=int, default=1000)
+ap.add_argument("--shuffles", type=int, default=20)
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--no-int", action="store_true")
 a = ap.parse_args()
@@ -23,7 +24,7 @@ kw = {"dynamic": {}, "markov1": dict(use_markov=True, p_win_after_win=0.75, p_wi
                                                dict(length=200, hit_rate=0.5, avg_win=100, avg_loss=100),
                                                dict(length=500, hit_rate=0.2, avg_win=100, avg_loss=200)])}[a.mode]
 eng = Engine(0)
-prm = make_params(0.82, 186.0, 219.0, a.trades, a.sims, 20, **kw)
+prm = make_params(0.82, 186.0, 219.0, a.trades, a.sims, a.shuffles, **kw)
 for r in range(a.reps):
     out = eng.simulate(prm, seed=100 + r, options=eng.options(chunk_paths=1 << 21, dedup=a.dedup, block_threads=a.block, int_fast_path=not a.no_int))
     t = eng.timing()

@@ -47,8 +47,8 @@ typedef enum {
     MCTS_ECUDA = -4,      /* CUDA runtime error, message has the details */
     MCTS_ENODEVICE = -5,  /* no usable CUDA device / wrong architecture: there is no CPU fallback */
     MCTS_EUNSUPPORTED = -6 /* valid for the reference but outside this build's limits (see message):
-                              > 16 distinct trade values (or > 8 of one sign), > ~260,000 trades per path,
-                              > 16 regimes, non-finite or subnormal trade values in simulate mode */
+                              > ~260,000 trades per path, > 16 regimes, non-finite or subnormal trade values
+                              in simulate mode, curve export of runs with > 16 distinct values */
 } mcts_status;
 
 /* Generator selection, same precedence as trading_models.py:477-490. */

@@ -283,4 +283,30 @@ MCTS_HD void gen_path_codes_fy(const GenSpec &g, uint64_t seed, uint32_t sim, ui
     }
 }
 
+// The same Fisher-Yates on plain fp64 values in global memory (runs with more distinct values than
+// 4-bit codes can name): vals[t * stride], base order = runs of each value in category order.
+MCTS_HD void gen_path_values_fy(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t k, const uint32_t *counts, double *vals, size_t stride)
+{
+    const uint32_t L = (uint32_t)g.L;
+    uint32_t t = 0;
+    for (int cat = 0; cat < g.K; cat++) {
+        const double v = g.val[cat];
+        for (uint32_t c = counts[cat]; c > 0 && t < L; c--, t++) vals[(size_t)t * stride] = v;
+    }
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t x[4] = {0, 0, 0, 0};
+    uint32_t have = 0xffffffffu;  // Philox block currently in x
+    for (uint32_t i = L - 1; i >= 1; i--) {
+        if ((i >> 2) != have) {
+            have = i >> 2;
+            philox4x32_10(k0, k1, have, k, sim, kStreamShuffle, x);
+        }
+        const uint32_t xi = (i & 3u) == 0u ? x[0] : (i & 3u) == 1u ? x[1] : (i & 3u) == 2u ? x[2] : x[3];
+        const uint32_t j = mulhi32(xi, i + 1u);
+        const double a = vals[(size_t)i * stride], b = vals[(size_t)j * stride];
+        vals[(size_t)i * stride] = b;
+        vals[(size_t)j * stride] = a;
+    }
+}
+
 }  // namespace mcts

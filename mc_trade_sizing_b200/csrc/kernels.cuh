@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __gr
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (local >= a.n) return;
     ValueSource src;
-    src.row = values + local * T;
+    src.row = values + local * T;  // `values` already points at this launch's first path
     run_pass<IDS, MODE>(src, a, local);
 }
 
@@ -269,6 +269,18 @@ __global__ void __launch_bounds__(kBlock) k_sequences(const __grid_constant__ Pa
         const uint32_t code = (codes[(size_t)(t >> 3) * cstride + tid] >> (4 * (t & 7))) & 15u;
         values[local * a.g.L + t] = a.g.tab[code].v1;
     }
+}
+
+// wide runs (more values than 4-bit codes): one thread per path shuffles its fp64 sequence in global
+// memory, values[local][t]; k_replay_pass then evaluates it.  Rare fallback, not tuned.
+static __global__ void __launch_bounds__(128) k_shuffle_values(const __grid_constant__ PathArgs a, double *__restrict__ values)
+{
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= a.n) return;
+    const int64_t path = a.path0 + local;
+    const int64_t sim = path / a.n_sh;
+    const uint32_t k = (uint32_t)(path - sim * a.n_sh);
+    gen_path_values_fy(a.g, a.seed, (uint32_t)sim, k, a.counts + (sim - a.sim0) * kMaxCat, values + local * a.g.L, 1);
 }
 
 // ---- exact-order reduction over the paths of one chunk --------------------------------------

@@ -424,6 +424,47 @@ static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
     return MCTS_OK;
 }
 
+// the evaluator passes over fp64 sequences values[a.n][T] already on the device
+static void launch_replay_passes(mcts_handle *h, cudaStream_t stream, int mode, const PathArgs &a, const double *values, int64_t T)
+{
+    const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+    if (mode == PM_DEDUP) {
+        k_replay_pass<DedupPass0, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
+        k_replay_pass<DedupPass1, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
+        k_replay_pass<DedupPass2, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
+        h->timing.launches += 3;
+    } else {
+        k_replay_pass<FullPass0, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
+        k_replay_pass<FullPass1, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
+        k_replay_pass<FullPass2, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
+        k_replay_pass<FullPass3, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
+        h->timing.launches += 4;
+    }
+}
+
+// Runs with more distinct values than 4-bit codes can name: shuffle fp64 sequences in global memory,
+// then the replay evaluator.  Sub-batches of at most 1 GiB of values.
+static int launch_wide(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
+{
+    if (mode == PM_CURVES) return fail(MCTS_EUNSUPPORTED, "curve export needs at most 16 distinct trade values (8 per sign)");
+    int64_t sub = (((int64_t)1 << 30) / ((int64_t)a.g.L * 8)) / 128 * 128;
+    if (sub < 128) return fail(MCTS_EUNSUPPORTED, "num_trades too large for a run with more than 16 distinct trade values");
+    sub = std::min<int64_t>(sub, (a.n + 127) / 128 * 128);
+    int rc = ensure(&h->d_values, &h->cap_values, sub * a.g.L);
+    if (rc) return rc;
+    for (int64_t off = 0; off < a.n; off += sub) {
+        PathArgs b = a;
+        b.path0 = a.path0 + off;
+        b.n = std::min<int64_t>(sub, a.n - off);
+        b.out_off = a.out_off + off;
+        k_shuffle_values<<<(unsigned)((b.n + 127) / 128), 128, 0, L.stream>>>(b, h->d_values);
+        h->timing.launches++;
+        launch_replay_passes(h, L.stream, mode, b, h->d_values, a.g.L);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return MCTS_OK;
+}
+
 static int launch_gen_base(mcts_handle *h, Lane &L, const GenSpec &g, uint64_t seed, int64_t sim0, int64_t n_sims)
 {
     int rc = ensure(&L.d_counts, &L.cap_sims, n_sims, sizeof(uint32_t) * kMaxCat);
@@ -510,7 +551,7 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
     int64_t max_n = 0;
     for (int64_t c = cb; c < ce; c++) max_n = std::max(max_n, count[c]);
     if (max_n == 0) return MCTS_OK;
-    const int n_lanes = (opt && opt->serial_chunks) || ce - cb < 2 ? 1 : 2;
+    const int n_lanes = (opt && opt->serial_chunks) || ce - cb < 2 || g.wide ? 1 : 2;  // the wide fallback shares one values buffer
     for (int l = 0; l < n_lanes; l++)
         if ((rc = ensure_out(h->lane[l], max_n))) return rc;
     if ((rc = ensure(&h->d_recs, &h->cap_recs, ce - cb))) return rc;
@@ -533,7 +574,7 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
         a.out = L.d_out;
         a.ld = L.cap_paths;
         if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
-        rc = launch_paths(h, L, mode, a);
+        rc = g.wide ? launch_wide(h, L, mode, a) : launch_paths(h, L, mode, a);
         if (rc) return rc;
         if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
         if ((rc = launch_reduce(h, L, n, f, h->d_recs + (c - cb)))) return rc;
@@ -603,20 +644,8 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
         a.sched = h->d_sched;
         a.out = L.d_out;
         a.ld = L.cap_paths;
-        const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
         if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
-        if (mode == PM_DEDUP) {
-            k_replay_pass<DedupPass0, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            k_replay_pass<DedupPass1, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            k_replay_pass<DedupPass2, PM_DEDUP><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            h->timing.launches += 3;
-        } else {
-            k_replay_pass<FullPass0, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            k_replay_pass<FullPass1, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            k_replay_pass<FullPass2, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            k_replay_pass<FullPass3, PM_FULL><<<grid, kBlock, 0, h->stream>>>(a, h->d_values, T);
-            h->timing.launches += 4;
-        }
+        launch_replay_passes(h, h->stream, mode, a, h->d_values, T);
         CUDA_TRY(cudaGetLastError());
         if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
         if ((rc = launch_reduce(h, L, n, f, h->d_recs + c))) return rc;
@@ -666,6 +695,16 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
     if (rc) return rc;
     const int L = a.g.L;
     if ((rc = ensure(&h->d_values, &h->cap_values, n * L))) return rc;
+    if (a.g.wide) {
+        k_shuffle_values<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a, h->d_values);
+        CUDA_TRY(cudaGetLastError());
+        h->timing.launches++;
+        CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(values, h->d_values, (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->timing.d2h_bytes += n * L * 8;
+        return timing_collect(h);
+    }
     size_t smem = (size_t)((L + 7) / 8) * kBlock * 4;
     const bool global = smem > 227 * 1024;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
@@ -705,6 +744,7 @@ int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int6
     PathArgs a;
     int rc = path_range_args(h, p, seed, first_path, n, &a);
     if (rc) return rc;
+    if (a.g.wide) return fail(MCTS_EUNSUPPORTED, "curve export needs at most 16 distinct trade values (8 per sign)");
     a.curves = curves_dev;
     a.out = nullptr;
     if ((rc = mark(h, h->stream, h->ev_paths, true))) return rc;

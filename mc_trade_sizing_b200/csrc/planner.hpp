@@ -75,7 +75,7 @@ struct SpecBuilder {
         s.cat_loss = category(-loss);
         if (s.cat_win < 0 || s.cat_loss < 0 || g.n_seg >= kMaxSeg) {
             status = MCTS_EUNSUPPORTED;
-            err = "more than 16 distinct trade values in one run (4-bit outcome codes)";
+            err = "more than 32 distinct trade values in one run";
             return false;
         }
         g.seg[g.n_seg++] = s;
@@ -148,17 +148,22 @@ inline int build_spec(const mcts_params &p, GenSpec *out, std::string *err)
         int n_win = 0, n_loss = 0;
         double vmax = 0;
         g.all_int = 1;
+        for (int k = 0; k < g.K; k++) {  // can every value get a 4-bit code (bit 0 = value > 0)?
+            const int idx = g.val[k] > 0 ? n_win++ : n_loss++;
+            if (idx >= 8 || k >= kMaxCodes) g.wide = 1;
+        }
+        n_win = n_loss = 0;
         for (int k = 0; k < g.K; k++) {
             const double v = g.val[k];
             const int win = v > 0;
             const int idx = win ? n_win++ : n_loss++;
-            if (idx >= 8) {
-                *err = "more than 8 distinct positive or 8 distinct non-positive trade values in one run (4-bit outcome codes)";
-                return MCTS_EUNSUPPORTED;
-            }
             if (v != 0.0 && !(fabs(v) >= 4.450147717014403e-308 && fabs(v) <= 8.98846567431158e+307)) {
                 *err = "trade values must be 0 or between 2^-1021 and 2^1023 in magnitude in simulate mode (use replay for such inputs)";
                 return MCTS_EUNSUPPORTED;
+            }
+            if (g.wide) {
+                g.all_int = 0;
+                continue;
             }
             const int code = (idx << 1) | win;
             if (k < 8) g.rank_codes |= (uint32_t)code << (4 * k);

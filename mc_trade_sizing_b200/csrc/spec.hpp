@@ -17,7 +17,8 @@
 namespace mcts {
 
 constexpr int kNumStrategies = 20;
-constexpr int kMaxCat = 16;       // distinct trade values per run (4-bit codes: <= 8 positive and <= 8 non-positive)
+constexpr int kMaxCat = 32;       // distinct trade values per run (16 regimes x {win, loss})
+constexpr int kMaxCodes = 16;     // of which the 4-bit code path handles 16 (<= 8 positive and <= 8 non-positive)
 constexpr int kMaxSeg = 20;       // 16 regimes, or the 3 phases + tail fill of :44-65
 constexpr int kMaxStackDepth = 12; // pairwise-tree depth over trades: T <= 128 * 2^11
 constexpr int kMaxLeaves = 4096;  // <= ~260,000 trades per path
@@ -47,7 +48,7 @@ struct GenSpec {
     int32_t cat_win, cat_loss;  // Markov modes
     uint32_t rank_codes;        // nibble r = 4-bit code of category r (r < 8)
     uint32_t rank_codes_hi;     // categories 8..15
-    int32_t pad0;
+    int32_t wide;               // more values than 4-bit codes can name: shuffle fp64 values in global memory instead
     int32_t all_int;            // every value integral and 6*max|v|*L < 2^31
     double val[kMaxCat];
     Tab tab[16];                // indexed by code

@@ -101,6 +101,17 @@ int h_simulate(const mcts_params *p, uint64_t seed, int mode, double *profit, do
         const uint32_t k = (uint32_t)(path % p->num_mc_shuffles);
         uint32_t cnt[kMaxCat];
         gen_base_counts(g, seed, (uint32_t)sim, cnt);
+        if (g.wide) {  // fp64 shuffle + replay evaluator, as launch_wide does on the device
+            std::vector<double> vals(g.L);
+            gen_path_values_fy(g, seed, (uint32_t)sim, k, cnt, vals.data(), 1);
+            if (seqs) memcpy(seqs + i * g.L, vals.data(), sizeof(double) * g.L);
+            if (profit) {
+                ValueSource src;
+                src.row = vals.data();
+                run_all(src, &sch, dedup, profit, dd, n, i);
+            }
+            continue;
+        }
         if (g.K <= 2) gen_path_codes<2>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
         else gen_path_codes_fy(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
         if (seqs)

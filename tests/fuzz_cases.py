@@ -25,7 +25,7 @@ def random_cases(n, seed):
             if rng.random() < 0.25:
                 kw = dict(use_regime=True, regimes=None)
             else:
-                nr = int(rng.integers(1, 7))
+                nr = int(rng.integers(1, 7)) if rng.random() < 0.8 else int(rng.integers(7, 17))
                 kw = dict(use_regime=True, regimes=[{"length": int(rng.integers(0, max(2, T))), "hit_rate": pick(),
                                                      "avg_win": val(), "avg_loss": val()} for _ in range(nr)])
         cases.append((tuple(args), kw))

@@ -71,8 +71,8 @@ def simulate(params, seed, first_path=0, n=None, dedup=False, want_eval=True, in
 
 
 def base_counts(params, seed, sim):
-    counts = (C.c_uint32 * 16)()
-    vals = np.zeros(16)
+    counts = (C.c_uint32 * 32)()
+    vals = np.zeros(32)
     K, L = C.c_int(), C.c_int()
     rc = lib().h_base_counts(C.byref(params), C.c_uint64(seed), sim, counts, _dp(vals), C.byref(K), C.byref(L))
     if rc != 0:

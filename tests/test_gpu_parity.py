@@ -150,7 +150,9 @@ def test_device_generator_matches_its_cpu_model(eng):
 def test_device_generator_matches_independent_restatement(eng):
     """GPU sequences == oracle/devgen_ref.c (plain C written from the generator specification)."""
     many = [{"length": 40 + 3 * i, "hit_rate": 0.3 + 0.04 * i, "avg_win": 50.0 + 10 * i, "avg_loss": 20.5 + 7 * i} for i in range(7)]
-    cases = _sim_cases() + [("regime_14_values", (0.82, 186.0, 219.0, 400, 30, 5), dict(use_regime=True, regimes=many))]
+    wide = [{"length": 20 + i, "hit_rate": 0.2 + 0.04 * i, "avg_win": 10.0 + 3 * i, "avg_loss": 5.5 + 2 * i} for i in range(16)]
+    cases = _sim_cases() + [("regime_14_values", (0.82, 186.0, 219.0, 400, 30, 5), dict(use_regime=True, regimes=many)),
+                            ("regime_32_values_fp64_fallback", (0.82, 186.0, 219.0, 440, 40, 5), dict(use_regime=True, regimes=wide))]
     for name, args, kw in cases:
         dev = eng.sequences(make_params(*args, **kw), seed=31337)
         ref = oracle.devgen_sequences(oracle.make_params(*args, **kw), 31337)
@@ -185,7 +187,7 @@ def test_fuzz_random_parameter_sets(eng):
         except _ffi.MctsError as e:
             assert e.code == _ffi.EUNSUPPORTED, (args, kw)
             vals = np.unique(ref_seqs)
-            assert (vals > 0).sum() > 8 or (vals <= 0).sum() > 8 or np.any((vals != 0) & (np.abs(vals) < 4.5e-308)), (args, kw)
+            assert np.any((vals != 0) & (np.abs(vals) < 4.5e-308)), (args, kw)   # only subnormal values are refused
             continue
         assert_bitexact(eng.sequences(prm, seed=99), ref_seqs, "%s %s" % (args, kw))
         exp = oracle.eval_paths(ref_seqs, num_trades=args[3])

@@ -285,8 +285,10 @@ static __global__ void __launch_bounds__(128) k_shuffle_values(const __grid_cons
 
 // ---- exact-order reduction over the paths of one chunk --------------------------------------
 
-// grid (ceil(2^d / 128), 40): partial[arr][j] = raw pairwise sum of node j at depth d
-static __global__ void __launch_bounds__(128) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
+// grid (ceil(2^d / 64), 40): partial[arr][j] = raw pairwise sum of node j at depth d.  64-thread blocks with
+// <= 64 registers fit beside three resident k_sim_paths blocks (4096 registers are left per SM), so
+// the reduction of one chunk really overlaps the path kernel of the next.
+static __global__ void __launch_bounds__(64) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int arr = blockIdx.y;
@@ -309,13 +311,14 @@ static __global__ void __launch_bounds__(128) k_reduce_nodes(const double *__res
 // grid 40 (one block per array): fold the 2^d node sums pairwise (the perfect-binary top of the
 // tree), level by level, ping-ponging between `part` row `arr` and scratch row 120 + arr; min / max
 // by block reduction.  The additions are exactly those of the sequential fold, only run in parallel.
-static __global__ void __launch_bounds__(256) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
+// 64 threads per block so that it, too, fits beside resident k_sim_paths blocks.
+static __global__ void __launch_bounds__(64) k_reduce_top(double *__restrict__ part, int64_t pstride, int d, mcts_chunk_result *__restrict__ rec, int64_t first_path, int64_t n)
 {
     const int arr = blockIdx.x, tid = threadIdx.x;
     double *p = part + (int64_t)arr * pstride, *q = part + (int64_t)(120 + arr) * pstride;
     const int64_t w0 = (int64_t)1 << d;
     for (int64_t w = w0; w > 1; w >>= 1) {
-        for (int64_t i = tid; i < (w >> 1); i += 256) q[i] = p[2 * i] + p[2 * i + 1];
+        for (int64_t i = tid; i < (w >> 1); i += 64) q[i] = p[2 * i] + p[2 * i + 1];
         __syncthreads();
         double *t = p;
         p = q;
@@ -323,15 +326,15 @@ static __global__ void __launch_bounds__(256) k_reduce_top(double *__restrict__ 
     }
     const double *pmn = part + (int64_t)(40 + arr) * pstride, *pmx = part + (int64_t)(80 + arr) * pstride;
     double mn = pmn[0], mx = pmx[0];
-    for (int64_t i = tid; i < w0; i += 256) {
+    for (int64_t i = tid; i < w0; i += 64) {
         mn = pmn[i] < mn ? pmn[i] : mn;
         mx = pmx[i] > mx ? pmx[i] : mx;
     }
-    __shared__ double smn[256], smx[256];
+    __shared__ double smn[64], smx[64];
     smn[tid] = mn;
     smx[tid] = mx;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = 32; s > 0; s >>= 1) {
         if (tid < s) {
             smn[tid] = smn[tid + s] < smn[tid] ? smn[tid + s] : smn[tid];
             smx[tid] = smx[tid + s] > smx[tid] ? smx[tid + s] : smx[tid];

@@ -286,7 +286,8 @@ def main():
             for sd in (1, 2):
                 eng.simulate(pm, seed=sd, options=eng.options(chunk_paths=CHUNK_PATHS))
             t = eng.timing()
-            eng.simulate(pm, seed=3, options=eng.options(chunk_paths=CHUNK_PATHS, int_fast_path=False))
+            for sd in (3, 4):   # first call loads the kernel; the second is timed
+                eng.simulate(pm, seed=sd, options=eng.options(chunk_paths=CHUNK_PATHS, int_fast_path=False))
             t64 = eng.timing()
             extras["other_configs"][name] = {"value": t["trade_steps"] / (t["total_ms"] * 1e-3),
                                              "value_fp64_evaluator": t64["trade_steps"] / (t64["total_ms"] * 1e-3), "unit": UNIT}
@@ -340,7 +341,7 @@ def main():
         "frac": achieved_tflops / peak_tflops,
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_sim_paths launch of this workload (2,097,160 paths), from the
         # committed `ncu --set full` capture profiles/r01_ncu_bench_sim_paths.txt; algorithmic bytes per launch = paths x 320 B
-        "traffic": 636.6e6, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
+        "traffic": 641.9e6, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
         "bound_note": "neither HBM (0.016 B per trade-step) nor tensor cores (no contraction) bound this kernel; SURVEY 8(d) "
                       "prescribes the SM issue / FP64-pipe roofline used here; the HBM roofline of curve-export mode is under curve_export",
         "definition": "achieved = 6 algorithmic fp64 ops per trade-step (SURVEY 8d) x trade-steps per launch / mean launch "

@@ -25,28 +25,29 @@ from . import engine as _engine
 
 # strategy descriptions, reference src/trading_models.py:451-472 (they are the `Strategy` column of
 # every downstream sink: dps.py:362)
-DESCRIPTIONS = {
-    1: "Constant position size 1",
-    2: "Increase to 2 after win, reset to 1 after loss",
-    3: "Increase to 2 after win, reset to 1 after loss or 2 wins",
-    4: "Increase to 2 after win, reset to 1 after loss or 3 wins",
-    5: "Increase to 2 after win, reset to 1 after loss or 4 wins",
-    6: "Increase to 2 after loss, reset to 1 after win",
-    7: "Increase to 2 after 2 losses, reset to 1 after win",
-    8: "Increase to 2 after 3 losses, reset to 1 after win",
-    9: "Pause after 1 win until next loss",
-    10: "Pause after 2 wins until next loss",
-    11: "Pause after 3 wins until next loss",
-    12: "Pause after 4 wins until next loss",
-    13: "Increase to 2 after 2 wins, reset to 1 after 2 losses",
-    14: "Increase to 2 after 1 win and 1 loss, else 1",
-    15: "Pause after 2 consecutive wins until 1 loss, then increase to 2",
-    16: "Increase to 2 after 2 losses, pause after 1 win until next loss",
-    17: "Increase to 2 after 1 win only if preceded by 1 loss, else 1",
-    18: "Increase to 3 after 3 wins, reset to 1 after 1 loss",
-    19: "Increase to 2 after 2 wins, to 3 after 2 losses, else 1",
-    20: "Increase to 2 after 1 win, to 3 after 2 losses, reset to 1 after win",
-}
+_DESCRIPTION_TEXT = (
+    "Constant position size 1",
+    "Increase to 2 after win, reset to 1 after loss",
+    "Increase to 2 after win, reset to 1 after loss or 2 wins",
+    "Increase to 2 after win, reset to 1 after loss or 3 wins",
+    "Increase to 2 after win, reset to 1 after loss or 4 wins",
+    "Increase to 2 after loss, reset to 1 after win",
+    "Increase to 2 after 2 losses, reset to 1 after win",
+    "Increase to 2 after 3 losses, reset to 1 after win",
+    "Pause after 1 win until next loss",
+    "Pause after 2 wins until next loss",
+    "Pause after 3 wins until next loss",
+    "Pause after 4 wins until next loss",
+    "Increase to 2 after 2 wins, reset to 1 after 2 losses",
+    "Increase to 2 after 1 win and 1 loss, else 1",
+    "Pause after 2 consecutive wins until 1 loss, then increase to 2",
+    "Increase to 2 after 2 losses, pause after 1 win until next loss",
+    "Increase to 2 after 1 win only if preceded by 1 loss, else 1",
+    "Increase to 3 after 3 wins, reset to 1 after 1 loss",
+    "Increase to 2 after 2 wins, to 3 after 2 losses, else 1",
+    "Increase to 2 after 1 win, to 3 after 2 losses, reset to 1 after win",
+)
+DESCRIPTIONS = {i + 1: text for i, text in enumerate(_DESCRIPTION_TEXT)}
 
 _engines: dict[int, "_engine.Engine"] = {}
 
@@ -97,153 +98,141 @@ def run_all_strategies(
     return summary_to_rows(out["summary"])
 
 
+_BREAK_EVEN_FACTOR = {"1st Order Markov": 1 + (0.7 - 0.5) / 5, "2nd Order Markov": 1 + (0.8 - 0.5) / 4,
+                      "Regime Switching": 1 + (0.6 - 0.5) / 3}
+
+
 def find_break_even_hit_rate(avg_win, avg_loss, mode):
-    """Reference src/trading_models.py:408-442 (printed by main(), scraped by dps.py:154)."""
+    """Reference src/trading_models.py:408-442 (printed by main(), scraped by dps.py:154): loss / (win + loss)
+    times the reference's hard-coded per-mode factor; None (after the reference's message) for invalid input."""
     if avg_win is None or avg_loss is None or avg_win <= 0 or avg_loss <= 0:
         print("❌ ERROR: Invalid values for avg_win or avg_loss! Calculation not possible.")
         return None
-    base_rate = avg_loss / (avg_win + avg_loss)
-    if base_rate == float("inf"):
+    rate = avg_loss / (avg_win + avg_loss)
+    if rate == float("inf"):
         print("❌ ERROR: Calculation resulted in an infinite value!")
         return None
-    if mode == "1st Order Markov":
-        base_rate *= (1 + (0.7 - 0.5) / 5)
-    elif mode == "2nd Order Markov":
-        base_rate *= (1 + (0.8 - 0.5) / 4)
-    elif mode == "Regime Switching":
-        base_rate *= (1 + (0.6 - 0.5) / 3)
-    return base_rate
+    factor = _BREAK_EVEN_FACTOR.get(mode)
+    return rate * factor if factor is not None else rate
+
+
+# The 16 command-line flags of the reference CLI (reference :533-550; dps.py:217-258 builds these
+# command lines): (name, type or None for a switch, default or REQUIRED, help text).
+REQUIRED = object()
+CLI_FLAGS = (
+    ("hit_rate", float, REQUIRED, "Hit rate, e.g. 0.7"),
+    ("avg_win", float, REQUIRED, "Average win per trade"),
+    ("avg_loss", float, REQUIRED, "Average loss per trade"),
+    ("num_simulations", int, 200, "Number of simulations (default: 200)"),
+    ("num_trades", int, 400, "Number of trades per simulation (default: 400)"),
+    ("num_mc_shuffles", int, 200, "Number of shuffles per simulation (default: 200)"),
+    ("use_markov", None, False, "Use Markov chain correlations (1st order)"),
+    ("p_win_after_win", float, 0.7, "P(win|win) for 1st order Markov model"),
+    ("p_win_after_loss", float, 0.5, "P(win|loss) for 1st order Markov model"),
+    ("use_markov2", None, False, "Use 2nd order Markov model"),
+    ("p_win_ww", float, 0.8, "P(win|win,win) for 2nd order Markov"),
+    ("p_win_wl", float, 0.6, "P(win|win,loss) for 2nd order Markov"),
+    ("p_win_lw", float, 0.5, "P(win|loss,win) for 2nd order Markov"),
+    ("p_win_ll", float, 0.3, "P(win|loss,loss) for 2nd order Markov"),
+    ("use_regime", None, False, "Use regime switching model"),
+    ("regimes", str, None, "Regime list as JSON string"),
+)
+
+# stdout layout of the reference table (:606-643; the scraper regex is dps.py:356)
+COLUMNS = (("Strategy", "<90", "<90"), ("Avg Profit (€)", ">14", "14.2f"), ("Avg Drawdown (€)", ">16", "16.2f"), ("Ratio", ">12", "12.2f"),
+           ("Min (€)", ">12", "12.2f"), ("Max (€)", ">12", "12.2f"), ("Min DD (€)", ">14", "14.2f"), ("Max DD (€)", ">14", "14.2f"),
+           ("Avg/Trade", ">12", "12.2f"), ("Profit/MaxDD", ">18", "18.2f"))
+MODE_NAMES = {"regime": "Regime Switching", "markov2": "2nd Order Markov", "markov1": "1st Order Markov", "none": "No Markov"}
 
 
 def build_parser():
-    """The 16 flags of reference :533-550, byte-compatible (dps.py:217-258 builds these command lines)."""
     parser = argparse.ArgumentParser(description="Simulate 20 trading strategies with/without Markov correlations, second-order Markov, and regime switching")
-    parser.add_argument("--hit_rate", type=float, required=True, help="Hit rate, e.g. 0.7")
-    parser.add_argument("--avg_win", type=float, required=True, help="Average win per trade")
-    parser.add_argument("--avg_loss", type=float, required=True, help="Average loss per trade")
-    parser.add_argument("--num_simulations", type=int, default=200, help="Number of simulations (default: 200)")
-    parser.add_argument("--num_trades", type=int, default=400, help="Number of trades per simulation (default: 400)")
-    parser.add_argument("--num_mc_shuffles", type=int, default=200, help="Number of shuffles per simulation (default: 200)")
-    parser.add_argument("--use_markov", action="store_true", help="Use Markov chain correlations (1st order)")
-    parser.add_argument("--p_win_after_win", type=float, default=0.7, help="P(win|win) for 1st order Markov model")
-    parser.add_argument("--p_win_after_loss", type=float, default=0.5, help="P(win|loss) for 1st order Markov model")
-    parser.add_argument("--use_markov2", action="store_true", help="Use 2nd order Markov model")
-    parser.add_argument("--p_win_ww", type=float, default=0.8, help="P(win|win,win) for 2nd order Markov")
-    parser.add_argument("--p_win_wl", type=float, default=0.6, help="P(win|win,loss) for 2nd order Markov")
-    parser.add_argument("--p_win_lw", type=float, default=0.5, help="P(win|loss,win) for 2nd order Markov")
-    parser.add_argument("--p_win_ll", type=float, default=0.3, help="P(win|loss,loss) for 2nd order Markov")
-    parser.add_argument("--use_regime", action="store_true", help="Use regime switching model")
-    parser.add_argument("--regimes", type=str, default=None, help="Regime list as JSON string")
+    for name, kind, default, text in CLI_FLAGS:
+        if kind is None:
+            parser.add_argument("--" + name, action="store_true", help=text)
+        elif default is REQUIRED:
+            parser.add_argument("--" + name, type=kind, required=True, help=text)
+        else:
+            parser.add_argument("--" + name, type=kind, default=default, help=text)
     return parser
 
 
-def _model_label(args):
-    pct = int(round(args.hit_rate * 100))
-    if args.use_regime:
-        return f"Hit rate: {pct}%  -  Regime Switching Model"
-    if args.use_markov2:
-        return f"Hit rate: {pct}%  -  2nd Order Markov"
-    if args.use_markov:
-        return f"Hit rate: {pct}%  -  1st Order Markov"
-    return f"Hit rate: {pct}%  -  No Markov"
+def _mode_key(args):
+    """generator precedence of the reference: regime > Markov-2 > Markov-1 > none (:477-490, :555-567)"""
+    return "regime" if args.use_regime else "markov2" if args.use_markov2 else "markov1" if args.use_markov else "none"
 
 
 def format_row(row):
     """One table row, reference :639-643 (matched by the scraper regex dps.py:356)."""
-    description, profit, dd, ratio, min_p, max_p, min_d, max_d, avg_per_trade, ratio_max_dd = row
-    return (
-        f"{description:<90} {profit:14.2f} {dd:16.2f} {ratio:12.2f} "
-        f"{min_p:12.2f} {max_p:12.2f} {min_d:14.2f} {max_d:14.2f} "
-        f"{avg_per_trade:12.2f} {ratio_max_dd:18.2f}"
-    )
+    return " ".join(format(value, spec) for value, (_, _, spec) in zip(row, COLUMNS))
+
+
+def settings_block(args):
+    """The header the scraper reads (dps.py:145-154): reference :552-584."""
+    key = _mode_key(args)
+    bar = "=" * 90
+    out = ["\n" + bar, "CURRENT SIMULATION SETTING:", f"Hit rate: {args.hit_rate:.2%}", "Mode: " + MODE_NAMES[key]]
+    if key == "regime" and args.regimes:
+        out.append(f"Regimes: {args.regimes}")
+    elif key == "markov2":
+        out.append(f"P(win|WW): {args.p_win_ww}, P(win|WL): {args.p_win_wl}, P(win|LW): {args.p_win_lw}, P(win|LL): {args.p_win_ll}")
+    elif key == "markov1":
+        out.append(f"P(win|win): {args.p_win_after_win}, P(win|loss): {args.p_win_after_loss}")
+    out.append(bar + "\n")
+    for label, value in (("Average win per trade: €", args.avg_win), ("Average loss per trade: €", args.avg_loss),
+                         ("Number of simulations: ", args.num_simulations), ("Number of trades per simulation: ", args.num_trades),
+                         ("Number of shuffles per simulation: ", args.num_mc_shuffles)):
+        out.append(f"{label}{value}")
+    breakeven = find_break_even_hit_rate(args.avg_win, args.avg_loss, MODE_NAMES[key])
+    out.append(f"Break-even hit rate: {breakeven:.2%}")
+    return out
 
 
 def main(argv=None):
     """stdout-compatible with reference :552-671 (settings block, break-even line, 20-row table,
-    rule after the third row, optional colorama 'Top 4' block)."""
+    rule after the third row, optional colorama 'Top 4' block); byte-for-byte equality with the
+    reference's output for the same rows is tested in tests/test_cli_cpu.py."""
     args = build_parser().parse_args(argv)
-
-    print("\n" + "=" * 90)
-    print("CURRENT SIMULATION SETTING:")
-    print(f"Hit rate: {args.hit_rate:.2%}")
-    if args.use_regime:
-        print("Mode: Regime Switching")
-        if args.regimes:
-            print(f"Regimes: {args.regimes}")
-    elif args.use_markov2:
-        print("Mode: 2nd Order Markov")
-        print(f"P(win|WW): {args.p_win_ww}, P(win|WL): {args.p_win_wl}, P(win|LW): {args.p_win_lw}, P(win|LL): {args.p_win_ll}")
-    elif args.use_markov:
-        print("Mode: 1st Order Markov")
-        print(f"P(win|win): {args.p_win_after_win}, P(win|loss): {args.p_win_after_loss}")
-    else:
-        print("Mode: No Markov")
-    print("=" * 90 + "\n")
-
-    print(f"Average win per trade: €{args.avg_win}")
-    print(f"Average loss per trade: €{args.avg_loss}")
-    print(f"Number of simulations: {args.num_simulations}")
-    print(f"Number of trades per simulation: {args.num_trades}")
-    print(f"Number of shuffles per simulation: {args.num_mc_shuffles}")
-
-    mode = "No Markov"
-    if args.use_regime:
-        mode = "Regime Switching"
-    elif args.use_markov2:
-        mode = "2nd Order Markov"
-    elif args.use_markov:
-        mode = "1st Order Markov"
-
-    breakeven = find_break_even_hit_rate(args.avg_win, args.avg_loss, mode)
-    print(f"Break-even hit rate: {breakeven:.2%}")
+    key = _mode_key(args)
+    for line in settings_block(args):
+        print(line)
 
     regimes = pyjson.loads(args.regimes) if args.use_regime and args.regimes else None
+    flags = {name: getattr(args, name) for name, kind, _, _ in CLI_FLAGS if name.startswith(("use_", "p_win_"))}
+    summary = run_all_strategies(args.hit_rate, args.avg_win, args.avg_loss, args.num_trades, args.num_simulations,
+                                 args.num_mc_shuffles, regimes=regimes, **flags)
 
-    summary = run_all_strategies(
-        args.hit_rate, args.avg_win, args.avg_loss, args.num_trades,
-        args.num_simulations, args.num_mc_shuffles,
-        use_markov=args.use_markov, p_win_after_win=args.p_win_after_win, p_win_after_loss=args.p_win_after_loss,
-        use_markov2=args.use_markov2, p_win_ww=args.p_win_ww, p_win_wl=args.p_win_wl,
-        p_win_lw=args.p_win_lw, p_win_ll=args.p_win_ll,
-        use_regime=args.use_regime, regimes=regimes,
-    )
-
+    header = " ".join(format(title, spec) for title, spec, _ in COLUMNS)
+    label = "Hit rate: %d%%  -  %s" % (int(round(args.hit_rate * 100)), MODE_NAMES[key] + (" Model" if key == "regime" else ""))
+    try:
+        from colorama import Fore, Style, init
+        paint = lambda colour, text: colour + text + Style.RESET_ALL
+    except ImportError:
+        Fore = init = None
+        paint = lambda colour, text: text
     print("\nResults (Monte Carlo, based on input parameters):\n")
-    header = (
-        f"{'Strategy':<90} {'Avg Profit (€)':>14} {'Avg Drawdown (€)':>16} {'Ratio':>12} "
-        f"{'Min (€)':>12} {'Max (€)':>12} {'Min DD (€)':>14} {'Max DD (€)':>14} "
-        f"{'Avg/Trade':>12} {'Profit/MaxDD':>18}"
-    )
     print(header)
     print("=" * len(header))
     print()
-    try:
-        from colorama import Fore, Style
-        print(Fore.YELLOW + f"*** {_model_label(args)} ***" + Style.RESET_ALL)
-    except ImportError:
-        print(f"*** {_model_label(args)} ***")
+    print(paint(Fore.YELLOW if Fore else None, f"*** {label} ***"))
     print()
-
     for idx, row in enumerate(summary):
         print(format_row(row))
         if idx == 2:
             print("-" * len(header))
 
-    try:
-        from colorama import Fore, Style, init
-        init(autoreset=True)
-        konst_idx = next((i for i, row in enumerate(summary) if row[0].startswith("Constant position size 1")), None)
-        print("\n\n\nTop 4 strategies compared to 'Constant position size 1':")
-        print("--------------------------------------------------------------")
-        for idx in range(4):
-            if idx >= len(summary):
-                break
-            print()
-            print(Fore.GREEN + format_row(summary[idx]) + Style.RESET_ALL)
-            if konst_idx is not None:
-                print(Fore.RED + format_row(summary[konst_idx]) + Style.RESET_ALL)
-    except ImportError:
-        pass
+    if Fore is None:
+        return
+    # the "Top 4" comparison block exists only when colorama is importable (:647-671)
+    init(autoreset=True)
+    baseline = next((row for row in summary if row[0].startswith(DESCRIPTIONS[1])), None)
+    print("\n\n\nTop 4 strategies compared to 'Constant position size 1':")
+    print("--------------------------------------------------------------")
+    for row in summary[:4]:
+        print()
+        print(paint(Fore.GREEN, format_row(row)))
+        if baseline is not None:
+            print(paint(Fore.RED, format_row(baseline)))
 
 
 if __name__ == "__main__":

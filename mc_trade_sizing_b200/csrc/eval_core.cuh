@@ -214,13 +214,43 @@ MCTS_HD void acc_init(Acc<NS> &a)
 // one trade of one strategy:  E += c;  r_j += c;  u = E - peak_old;  peak = max;  dd = min(dd, u)
 // (u <= 0 is exactly the reference's E_t - peak_t; when u > 0 the reference records +0.0, which
 // never lowers dd because dd <= 0 from the first trade on)
+#if defined(__CUDACC__) && defined(MCTS_PSEL)
+// 64-bit conditional moves as predicated IMADs (FMA pipe) instead of FSEL pairs (ALU pipe, the
+// saturated port).  The multiplier 1 and addend 0 come from constant memory so that ptxas cannot
+// fold the multiply-add into a move (which it would turn back into selects).
+static __constant__ uint32_t c_sel_one = 1u, c_sel_zero = 0u;
+__device__ __forceinline__ void psel_gt0(double &dst, double u, double src)
+{
+    asm("{ .reg .pred p; .reg .b32 lo, hi, slo, shi;\n\t"
+        "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+        "mov.b64 {lo,hi}, %0;\n\tmov.b64 {slo,shi}, %2;\n\t"
+        "@p mad.lo.u32 lo, slo, %3, %4;\n\t@p mad.lo.u32 hi, shi, %3, %4;\n\t"
+        "mov.b64 %0, {lo,hi}; }"
+        : "+d"(dst) : "d"(u), "d"(src), "r"(c_sel_one), "r"(c_sel_zero));
+}
+__device__ __forceinline__ void psel_lt(double &dst, double u)
+{
+    asm("{ .reg .pred p; .reg .b32 lo, hi, slo, shi;\n\t"
+        "setp.lt.f64 p, %1, %0;\n\t"
+        "mov.b64 {lo,hi}, %0;\n\tmov.b64 {slo,shi}, %1;\n\t"
+        "@p mad.lo.u32 lo, slo, %2, %3;\n\t@p mad.lo.u32 hi, shi, %2, %3;\n\t"
+        "mov.b64 %0, {lo,hi}; }"
+        : "+d"(dst) : "d"(u), "r"(c_sel_one), "r"(c_sel_zero));
+}
+#endif
+
 MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double c)
 {
     E = E + c;
     rj = rj + c;
     const double u = E - peak;
+#if defined(__CUDA_ARCH__) && defined(MCTS_PSEL)
+    if (MCTS_PSEL & 1) psel_gt0(peak, u, E); else peak = (u > 0.0) ? E : peak;
+    if (MCTS_PSEL & 2) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
+#else
     peak = (u > 0.0) ? E : peak;
     dd = (u < dd) ? u : dd;
+#endif
 }
 
 // A full block of 8 trades.  SRC provides, per trade i, the three tabulated contributions.
@@ -332,33 +362,66 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
 // When every trade value is an integer and 6 * max|v| * L < 2^31 (checked on the host), equity, peak
 // and drawdown are exact integers below 2^30 in magnitude, every summation order gives the same
 // value (profit == final equity) and the fp64 results of the reference are reproduced exactly by
-// converting the int32 results at the end.  Five integer instructions per trade-step instead of
-// eleven fp64/select instructions; same masks, same rules.
+// converting the int32 results at the end.  Same masks, same rules.
+//
+// One pass evaluates ALL strategies of the launch (20 ids = 60 registers of state), so the code word,
+// the masks, the table lookup and the predicate tests of a trade are paid once per trade, not once per
+// five strategies.  The contribution is never selected: the equity takes one unconditional and up to
+// two predicated integer multiply-adds (E += v*1, on the FMA pipe: `one` comes from constant memory so
+// that ptxas keeps the IMAD), which leaves only the running minimum and maximum (VIADDMNMX + VIMNMX)
+// on the ALU pipe: ~2.3 ALU and ~1.7 FMA instructions per trade-step.
 struct IntTab {
-    int32_t v1, v2, v3, pad;
+    int32_t v1, v2;  // v, 2v
 };
 
-template <int RULE>
-MCTS_HD int32_t contribution_i(const Preds &p, int32_t v1, int32_t v2, int32_t v3)
+#if defined(__CUDACC__)
+static __constant__ int32_t c_int_one = 1;
+// Twenty zeros the compiler cannot see through: start values of the equities when all 20 ids are to be
+// evaluated for real (ids of one behaviour class would otherwise be merged into one chain).
+static __constant__ int32_t c_int_zero[kNumStrategies] = {};
+#endif
+
+MCTS_HD void iadd(int32_t &E, int32_t v)
 {
-    if constexpr (RULE == R_C1) return v1;
-    if constexpr (RULE == R_AM) return p.pw ? v2 : v1;
-    if constexpr (RULE == R_F1) return p.fw ? v2 : v1;
-    if constexpr (RULE == R_MG) return p.pl ? v2 : v1;
-    if constexpr (RULE == R_MG2) return p.pll ? v2 : v1;
-    if constexpr (RULE == R_P1) return p.pw ? 0 : v1;
-    if constexpr (RULE == R_P2) return p.pww ? 0 : v1;
-    if constexpr (RULE == R_S16) return p.pw ? 0 : (p.s16 ? v2 : v1);
-    if constexpr (RULE == R_S18) return p.pww ? v3 : v1;
-    if constexpr (RULE == R_S19) return p.pll ? v3 : (p.pww ? v2 : v1);
-    if constexpr (RULE == R_S20) return p.pll ? v3 : v1;
-    return v1;
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(E) : "r"(v), "r"(c_int_one));
+#else
+    E += v;
+#endif
+}
+MCTS_HD void iadd_if(int32_t &E, int32_t v, bool p)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{ .reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q mad.lo.s32 %0, %1, %2, %0; }" : "+r"(E) : "r"(v), "r"(c_int_one), "r"((uint32_t)p));
+#else
+    if (p) E += v;
+#endif
+}
+
+// E += size * v, size in {0, 1, 2, 3} by the behaviour's rule (cf. contribution<RULE>)
+template <int RULE>
+MCTS_HD void add_contribution_i(int32_t &E, const Preds &p, int32_t v1, int32_t v2)
+{
+    if constexpr (RULE == R_C1) iadd(E, v1);
+    if constexpr (RULE == R_AM) { iadd(E, v1); iadd_if(E, v1, p.pw); }
+    if constexpr (RULE == R_F1) { iadd(E, v1); iadd_if(E, v1, p.fw); }
+    if constexpr (RULE == R_MG) { iadd(E, v1); iadd_if(E, v1, p.pl); }
+    if constexpr (RULE == R_MG2) { iadd(E, v1); iadd_if(E, v1, p.pll); }
+    if constexpr (RULE == R_P1) iadd_if(E, v1, !p.pw);
+    if constexpr (RULE == R_P2) iadd_if(E, v1, !p.pww);
+    if constexpr (RULE == R_S16) { iadd_if(E, v1, !p.pw); iadd_if(E, v1, p.s16); }  // s16 implies !pw
+    if constexpr (RULE == R_S18) { iadd(E, v1); iadd_if(E, v2, p.pww); }
+    if constexpr (RULE == R_S19) { iadd(E, v1); iadd_if(E, v1, p.pww); iadd_if(E, v2, p.pll); }  // pww, pll exclusive
+    if constexpr (RULE == R_S20) { iadd(E, v1); iadd_if(E, v2, p.pll); }
 }
 
 MCTS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 MCTS_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
 
-template <class IDS>
+using FullAll = IdList<1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20>;
+using DedupAll = IdList<1, 2, 4, 6, 8, 9, 11, 16, 18, 19, 20>;
+
+template <class IDS, bool OPAQUE_START = false>
 MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab, int L, int32_t (&profit)[IDS::N], int32_t (&drawdown)[IDS::N])
 {
     constexpr int NS = IDS::N;
@@ -366,6 +429,9 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         E[s] = 0;
+#if defined(__CUDA_ARCH__)
+        if constexpr (OPAQUE_START) E[s] = c_int_zero[s];
+#endif
         peak[s] = -(1 << 30);  // below any reachable equity; E_0 - peak cannot overflow
         dd[s] = 0;
     }
@@ -385,7 +451,7 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                E[s] += contribution_i<rule>(p, t.v1, t.v2, t.v3);
+                add_contribution_i<rule>(E[s], p, t.v1, t.v2);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });
@@ -404,7 +470,7 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                E[s] += contribution_i<rule>(p, t.v1, t.v2, t.v3);
+                add_contribution_i<rule>(E[s], p, t.v1, t.v2);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });

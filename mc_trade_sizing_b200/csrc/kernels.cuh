@@ -186,7 +186,7 @@ template <class IDS, int MODE>
 __device__ __forceinline__ void run_pass_int(const uint32_t *codes, int stride, const IntTab *tab, const PathArgs &a, int64_t local)
 {
     int32_t profit[IDS::N], dd[IDS::N];
-    eval_path_int<IDS>(codes, stride, tab, a.g.L, profit, dd);
+    eval_path_int<IDS, MODE != PM_DEDUP>(codes, stride, tab, a.g.L, profit, dd);
     static_for<IDS::N>([&](auto S) {
         constexpr int s = decltype(S)::value;
         constexpr int id = IDS::id(s);
@@ -217,31 +217,16 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(
         IntTab t;
         t.v1 = v;
         t.v2 = 2 * v;
-        t.v3 = 3 * v;
-        t.pad = 0;
         tab[tid] = t;
     }
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
     const bool active = local < a.n;
     if (active) generate_codes<K>(a, local, codes + tid, BLOCK);
-    if constexpr (MODE == PM_DEDUP) {
-        __syncthreads();
-        if (active) run_pass_int<DedupPass0, MODE>(codes + tid, BLOCK, tab, a, local);
-        __syncthreads();
-        if (active) run_pass_int<DedupPass1, MODE>(codes + tid, BLOCK, tab, a, local);
-        __syncthreads();
-        if (active) run_pass_int<DedupPass2, MODE>(codes + tid, BLOCK, tab, a, local);
-    } else {
-        __syncthreads();
-        if (active) run_pass_int<FullPass0, MODE>(codes + tid, BLOCK, tab, a, local);
-        __syncthreads();
-        if (active) run_pass_int<FullPass1, MODE>(codes + tid, BLOCK, tab, a, local);
-        __syncthreads();
-        if (active) run_pass_int<FullPass2, MODE>(codes + tid, BLOCK, tab, a, local);
-        __syncthreads();
-        if (active) run_pass_int<FullPass3, MODE>(codes + tid, BLOCK, tab, a, local);
-    }
+    __syncthreads();  // phase alignment only (the code column is thread-private)
+    if (!active) return;
+    if constexpr (MODE == PM_DEDUP) run_pass_int<DedupAll, MODE>(codes + tid, BLOCK, tab, a, local);
+    else run_pass_int<FullAll, MODE>(codes + tid, BLOCK, tab, a, local);
 }
 
 // replay: values [n][T] row-major fp64 in device memory, one pass (five strategies) per launch

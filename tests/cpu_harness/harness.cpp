@@ -118,17 +118,9 @@ int h_simulate(const mcts_params *p, uint64_t seed, int mode, double *profit, do
             for (int t = 0; t < g.L; t++) seqs[i * g.L + t] = g.tab[(codes[t >> 3] >> (4 * (t & 7))) & 15].v1;
         if (profit && want_int && g.all_int) {
             IntTab tab[16];
-            for (int c = 0; c < 16; c++) tab[c] = IntTab{g.ival[c], 2 * g.ival[c], 3 * g.ival[c], 0};
-            if (dedup) {
-                run_pass_int<DedupPass0, true>(codes.data(), tab, g.L, profit, dd, n, i);
-                run_pass_int<DedupPass1, true>(codes.data(), tab, g.L, profit, dd, n, i);
-                run_pass_int<DedupPass2, true>(codes.data(), tab, g.L, profit, dd, n, i);
-            } else {
-                run_pass_int<FullPass0, false>(codes.data(), tab, g.L, profit, dd, n, i);
-                run_pass_int<FullPass1, false>(codes.data(), tab, g.L, profit, dd, n, i);
-                run_pass_int<FullPass2, false>(codes.data(), tab, g.L, profit, dd, n, i);
-                run_pass_int<FullPass3, false>(codes.data(), tab, g.L, profit, dd, n, i);
-            }
+            for (int c = 0; c < 16; c++) tab[c] = IntTab{g.ival[c], 2 * g.ival[c]};
+            if (dedup) run_pass_int<DedupAll, true>(codes.data(), tab, g.L, profit, dd, n, i);
+            else run_pass_int<FullAll, false>(codes.data(), tab, g.L, profit, dd, n, i);
         } else if (profit) {
             CodeSource src;
             src.codes = codes.data();

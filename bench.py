@@ -302,7 +302,8 @@ def main():
         t = eng.timing()
         extras["replay"] = {"e2e_value": t["trade_steps"] / wall, "kernels_value": t["trade_steps"] / (t["paths_ms"] * 1e-3), "unit": UNIT,
                             "h2d_bytes": int(t["h2d_bytes"]), "d2h_bytes": int(t["d2h_bytes"]), "paths": n_rep,
-                            "note": "replay of caller-supplied fp64 sequences: 8 B per (path, trade) cross PCIe from pageable host memory"}
+                            "note": "replay of caller-supplied fp64 sequences: 8 B per (path, trade) cross PCIe from pageable host memory, staged by "
+                                    "worker threads through pinned slices (csrc/stager.hpp)"}
         del seqs
         # (b) equity-curve export: HBM-bound, 8 B per trade-step
         n_curve = 1 << 17

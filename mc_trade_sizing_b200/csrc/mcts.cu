@@ -13,6 +13,7 @@
 #include "../../include/mcts.h"
 #include "kernels.cuh"
 #include "planner.hpp"
+#include "stager.hpp"
 
 using namespace mcts;
 
@@ -63,8 +64,11 @@ struct mcts_handle {
     int64_t cap_recs = 0;
     LeafSched *d_sched = nullptr;
     int64_t sched_L = -1;
-    double *d_values = nullptr;
-    int64_t cap_values = 0;
+    // replay: two staging areas for caller sequences (chunk c+1 is copied while chunk c is evaluated)
+    double *d_values[2] = {nullptr, nullptr};
+    int64_t cap_values[2] = {0, 0};
+    cudaEvent_t values_free[2] = {nullptr, nullptr};  // recorded after the kernels that read d_values[i]
+    Stager stager;
     // event pool + timing of the last call
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -210,7 +214,11 @@ void mcts_destroy(mcts_handle *h)
     }
     cudaFree(h->d_recs);
     cudaFree(h->d_sched);
-    cudaFree(h->d_values);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->d_values[i]);
+        if (h->values_free[i]) cudaEventDestroy(h->values_free[i]);
+    }
+    h->stager.destroy();
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
@@ -450,16 +458,16 @@ static int launch_wide(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
     int64_t sub = (((int64_t)1 << 30) / ((int64_t)a.g.L * 8)) / 128 * 128;
     if (sub < 128) return fail(MCTS_EUNSUPPORTED, "num_trades too large for a run with more than 16 distinct trade values");
     sub = std::min<int64_t>(sub, (a.n + 127) / 128 * 128);
-    int rc = ensure(&h->d_values, &h->cap_values, sub * a.g.L);
+    int rc = ensure(&h->d_values[0], &h->cap_values[0], sub * a.g.L);
     if (rc) return rc;
     for (int64_t off = 0; off < a.n; off += sub) {
         PathArgs b = a;
         b.path0 = a.path0 + off;
         b.n = std::min<int64_t>(sub, a.n - off);
         b.out_off = a.out_off + off;
-        k_shuffle_values<<<(unsigned)((b.n + 127) / 128), 128, 0, L.stream>>>(b, h->d_values);
+        k_shuffle_values<<<(unsigned)((b.n + 127) / 128), 128, 0, L.stream>>>(b, h->d_values[0]);
         h->timing.launches++;
-        launch_replay_passes(h, L.stream, mode, b, h->d_values, a.g.L);
+        launch_replay_passes(h, L.stream, mode, b, h->d_values[0], a.g.L);
         CUDA_TRY(cudaGetLastError());
     }
     return MCTS_OK;
@@ -629,12 +637,19 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
     int64_t max_n = *std::max_element(count.begin(), count.end());
     Lane &L = h->lane[0];
     if ((rc = ensure_out(L, max_n))) return rc;
-    if ((rc = ensure(&h->d_values, &h->cap_values, max_n * T))) return rc;
+    const int n_buf = nc > 1 ? 2 : 1;
+    for (int i = 0; i < n_buf; i++) {
+        if ((rc = ensure(&h->d_values[i], &h->cap_values[i], max_n * T))) return rc;
+        if (!h->values_free[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->values_free[i], cudaEventDisableTiming));
+    }
+    if (!h->stager.ready()) CUDA_TRY(h->stager.init(h->device));
     if ((rc = ensure(&h->d_recs, &h->cap_recs, nc))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
     for (int64_t c = 0; c < nc; c++) {
         const int64_t f = first[c], n = count[c];
-        CUDA_TRY(cudaMemcpyAsync(h->d_values, values + f * T, (size_t)n * T * 8, cudaMemcpyHostToDevice, h->stream));
+        double *d_vals = h->d_values[c % n_buf];
+        // pageable caller memory -> pinned slices -> device, by the stager's worker threads (stager.hpp)
+        CUDA_TRY(h->stager.copy(d_vals, values + f * T, (size_t)n * T * 8, c >= n_buf ? h->values_free[c % n_buf] : nullptr, h->stream));
         h->timing.h2d_bytes += n * T * 8;
         PathArgs a;
         memset(&a, 0, sizeof a);
@@ -645,9 +660,10 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
         a.out = L.d_out;
         a.ld = L.cap_paths;
         if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
-        launch_replay_passes(h, h->stream, mode, a, h->d_values, T);
+        launch_replay_passes(h, h->stream, mode, a, d_vals, T);
         CUDA_TRY(cudaGetLastError());
         if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
+        CUDA_TRY(cudaEventRecord(h->values_free[c % n_buf], h->stream));
         if ((rc = launch_reduce(h, L, n, f, h->d_recs + c))) return rc;
         if ((rc = copy_paths_out(h, L, f, n, P, profit, dd))) return rc;
         h->timing.trade_steps += n * T * MCTS_NSTRAT;
@@ -694,13 +710,13 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
     int rc = path_range_args(h, p, seed, first_path, n, &a);
     if (rc) return rc;
     const int L = a.g.L;
-    if ((rc = ensure(&h->d_values, &h->cap_values, n * L))) return rc;
+    if ((rc = ensure(&h->d_values[0], &h->cap_values[0], n * L))) return rc;
     if (a.g.wide) {
-        k_shuffle_values<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a, h->d_values);
+        k_shuffle_values<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a, h->d_values[0]);
         CUDA_TRY(cudaGetLastError());
         h->timing.launches++;
         CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(values, h->d_values, (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(values, h->d_values[0], (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->timing.d2h_bytes += n * L * 8;
         return timing_collect(h);
@@ -719,10 +735,10 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
 #define LAUNCH_SEQ(KK)                                                                                                        \
     do {                                                                                                                      \
         if (global) {                                                                                                         \
-            k_sequences<KK, true><<<grid, kBlock, 0, h->stream>>>(a, h->d_values);                                            \
+            k_sequences<KK, true><<<grid, kBlock, 0, h->stream>>>(a, h->d_values[0]);                                            \
         } else {                                                                                                              \
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sequences<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-            k_sequences<KK, false><<<grid, kBlock, smem, h->stream>>>(a, h->d_values);                                        \
+            k_sequences<KK, false><<<grid, kBlock, smem, h->stream>>>(a, h->d_values[0]);                                        \
         }                                                                                                                     \
     } while (0)
     if (a.g.K <= 2) LAUNCH_SEQ(2);
@@ -731,7 +747,7 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
     CUDA_TRY(cudaGetLastError());
     h->timing.launches++;
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(values, h->d_values, (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(values, h->d_values[0], (size_t)n * L * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->timing.d2h_bytes += n * L * 8;
     return timing_collect(h);

@@ -32,6 +32,7 @@ CHUNK_PATHS = 1 << 22          # the library default: two 4.19 M-path chunks per
 METRIC = "trade-steps/sec (paths x trades x strategies)"
 UNIT = "trade-steps/s"
 FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)
+TRAFFIC_PER_LAUNCH = 641.9e6         # dram bytes read + written by one k_sim_paths launch (ncu --set full, profiles/)
 
 
 def workload_config(n_gpus):
@@ -342,7 +343,7 @@ def main():
         "frac": achieved_tflops / peak_tflops,
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_sim_paths launch of this workload (2,097,160 paths), from the
         # committed `ncu --set full` capture profiles/r01_ncu_bench_sim_paths.txt; algorithmic bytes per launch = paths x 320 B
-        "traffic": 641.9e6, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
+        "traffic": TRAFFIC_PER_LAUNCH, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
         "bound_note": "neither HBM (0.016 B per trade-step) nor tensor cores (no contraction) bound this kernel; SURVEY 8(d) "
                       "prescribes the SM issue / FP64-pipe roofline used here; the HBM roofline of curve-export mode is under curve_export",
         "definition": "achieved = 6 algorithmic fp64 ops per trade-step (SURVEY 8d) x trade-steps per launch / mean launch "
@@ -353,9 +354,12 @@ def main():
         "kernel_share_of_step": kstat["paths_ms"] / max(kstat["total_ms"], 1e-9),
         "int_alu_inst_per_s": peaks["int_inst_per_s"], "fp64_inst_per_s": peaks["fp64_inst_per_s"],
         "sm_clock_mhz_microbench": peaks["sm_clock_mhz"],
-        # what the evaluator's instruction mix can reach on this chip: register-only replica of the trade step at the same
-        # occupancy (mcts_measure_step_ceiling): DSETP and the ALU-pipe selects do not overlap, so the step costs ~16 cycles
-        "mix_ceiling": {"strategy_steps_per_s": peaks["step_ceiling_per_s"], "kernel_frac": kernel_rate / peaks["step_ceiling_per_s"]},
+        # register-only replica of the SELECT-based trade step (3 DADD + 2 DSETP + 5 FSEL per strategy-step, no generator, no
+        # shared memory, no stores) at the kernel's occupancy, measured in this process (mcts_measure_step_ceiling).  It
+        # saturates the ALU pipe; the shipped kernel moves the peak / drawdown selects to the FMA pipe as predicated IMADs
+        # (DESIGN.md section 5), so it is no longer bounded by this figure -- kept as a reference point
+        "mix_ceiling": {"strategy_steps_per_s": peaks["step_ceiling_per_s"], "kernel_frac": kernel_rate / peaks["step_ceiling_per_s"],
+                        "note": "select-based replica (ALU-pipe bound); the kernel uses FMA-pipe predicated moves instead"},
         "hbm_note": "aggregate mode moves 0.016 B per trade-step (per-path results only); HBM bounds only curve export",
     }
 

@@ -214,7 +214,7 @@ MCTS_HD void acc_init(Acc<NS> &a)
 // one trade of one strategy:  E += c;  r_j += c;  u = E - peak_old;  peak = max;  dd = min(dd, u)
 // (u <= 0 is exactly the reference's E_t - peak_t; when u > 0 the reference records +0.0, which
 // never lowers dd because dd <= 0 from the first trade on)
-#if defined(__CUDACC__) && defined(MCTS_PSEL)
+#if defined(__CUDACC__)
 // 64-bit conditional moves as predicated IMADs (FMA pipe) instead of FSEL pairs (ALU pipe, the
 // saturated port).  The multiplier 1 and addend 0 come from constant memory so that ptxas cannot
 // fold the multiply-add into a move (which it would turn back into selects).
@@ -239,14 +239,16 @@ __device__ __forceinline__ void psel_lt(double &dst, double u)
 }
 #endif
 
+// SEL: bit 0 = peak, bit 1 = drawdown updated by predicated IMAD moves (device only); 0 = plain selects
+template <int SEL = 0>
 MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double c)
 {
     E = E + c;
     rj = rj + c;
     const double u = E - peak;
-#if defined(__CUDA_ARCH__) && defined(MCTS_PSEL)
-    if (MCTS_PSEL & 1) psel_gt0(peak, u, E); else peak = (u > 0.0) ? E : peak;
-    if (MCTS_PSEL & 2) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
+#if defined(__CUDA_ARCH__)
+    if constexpr ((SEL & 1) != 0) psel_gt0(peak, u, E); else peak = (u > 0.0) ? E : peak;
+    if constexpr ((SEL & 2) != 0) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
 #else
     peak = (u > 0.0) ? E : peak;
     dd = (u < dd) ? u : dd;
@@ -262,7 +264,7 @@ struct NoSink {
     }
 };
 
-template <class IDS, bool BINARY, class SRC, class SINK>
+template <class IDS, bool BINARY, int SEL, class SRC, class SINK>
 MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t0)
 {
     const Masks m = BINARY ? make_masks_binary(W, a.h) : make_masks(W, W ^ 0x11111111u, a.h);
@@ -275,7 +277,7 @@ MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
             const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
-            trade_step(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
+            trade_step<SEL>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     });
@@ -283,7 +285,7 @@ MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t
 
 // The < 8 trades after the last full block: added one by one to the leaf result (the n % 8 loop
 // of the pairwise leaf, or the whole n < 8 case).  W/Lb bits beyond `count` are ignored.
-template <class IDS, class SRC, class SINK>
+template <class IDS, int SEL, class SRC, class SINK>
 MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32_t Lb, int count, SRC &src, SINK &sink, int t0)
 {
     const Masks m = make_masks(W, Lb, a.h);
@@ -295,7 +297,7 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
             const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
-            trade_step(a.E[s], a.peak[s], a.dd[s], res[s], c);
+            trade_step<SEL>(a.E[s], a.peak[s], a.dd[s], res[s], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     }
@@ -305,7 +307,7 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
 //   SRC: uint32_t load(int oct)       -> win bits of block `oct` (and latches its values)
 //        uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
 //        get<i>() / get_dyn(i)
-template <class IDS, class SRC, class SINK>
+template <class IDS, int SEL = 0, class SRC, class SINK>
 MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, double (&profit)[IDS::N], double (&drawdown)[IDS::N])
 {
     constexpr int NS = IDS::N;
@@ -318,7 +320,7 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
     const int n_leaves = sch->n_leaves;
     if (sch->n_oct > 0) {  // first block: three-valued history ("nothing before the first trade")
         const uint32_t W = src.load(0);
-        eval_block8<IDS, false>(a, W, src, sink, 0);
+        eval_block8<IDS, false, SEL>(a, W, src, sink, 0);
         oct = 1;
     }
     for (int leaf = 0; leaf < n_leaves; leaf++) {
@@ -327,7 +329,7 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
         leaf_start = end;
         for (; oct < end; oct++) {
             const uint32_t W = src.load(oct);
-            eval_block8<IDS, true>(a, W, src, sink, oct * 8);
+            eval_block8<IDS, true, SEL>(a, W, src, sink, oct * 8);
         }
 #pragma unroll
         for (int s = 0; s < NS; s++) {
@@ -339,7 +341,7 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
         if (leaf == n_leaves - 1 && sch->tail > 0) {
             uint32_t Lb;
             const uint32_t W = src.load_tail(oct, sch->tail, &Lb);
-            eval_tail<IDS>(a, res, W, Lb, sch->tail, src, sink, oct * 8);
+            eval_tail<IDS, SEL>(a, res, W, Lb, sch->tail, src, sink, oct * 8);
         }
         int merges = sch->merges[leaf];
 #pragma unroll

@@ -32,6 +32,22 @@ constexpr int kTabWords = 16 * sizeof(Tab) / 4;
 
 enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
 
+// How peak / drawdown are updated in each kernel flavour (eval_core.cuh trade_step<SEL>): predicated
+// IMAD moves on the FMA pipe (3) where that measured faster on the B200, select pairs (0) elsewhere.
+#ifndef MCTS_SEL_FULL
+#define MCTS_SEL_FULL 3    // +4.4 %: the select version saturates the ALU pipe
+#endif
+#ifndef MCTS_SEL_DEDUP
+#define MCTS_SEL_DEDUP 0   // 4-strategy passes: predicated moves measured 10 % slower
+#endif
+#ifndef MCTS_SEL_CURVES
+#define MCTS_SEL_CURVES 0  // HBM-bound
+#endif
+#ifndef MCTS_SEL_REPLAY
+#define MCTS_SEL_REPLAY 0
+#endif
+__host__ __device__ constexpr int sel_of_mode(int mode) { return mode == PM_FULL ? MCTS_SEL_FULL : mode == PM_DEDUP ? MCTS_SEL_DEDUP : MCTS_SEL_CURVES; }
+
 struct PathArgs {
     GenSpec g;
     uint64_t seed;
@@ -84,7 +100,7 @@ struct CurveSink {
     }
 };
 
-template <class IDS, int MODE, class SRC>
+template <class IDS, int MODE, int SEL, class SRC>
 __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t local)
 {
     double profit[IDS::N], dd[IDS::N];
@@ -95,10 +111,10 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
         sink.local = local;
         sink.L = a.g.L;
         sink.half = (a.g.L + 1) >> 1;
-        eval_path<IDS>(src, sink, a.sched, profit, dd);
+        eval_path<IDS, SEL>(src, sink, a.sched, profit, dd);
     } else {
         NoSink sink;
-        eval_path<IDS>(src, sink, a.sched, profit, dd);
+        eval_path<IDS, SEL>(src, sink, a.sched, profit, dd);
     }
     if (a.out == nullptr) return;
     static_for<IDS::N>([&](auto S) {
@@ -164,20 +180,20 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
     src.word = 0;
     if constexpr (MODE == PM_DEDUP) {
         __syncthreads();
-        if (active) run_pass<DedupPass0, MODE>(src, a, local);
+        if (active) run_pass<DedupPass0, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
-        if (active) run_pass<DedupPass1, MODE>(src, a, local);
+        if (active) run_pass<DedupPass1, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
-        if (active) run_pass<DedupPass2, MODE>(src, a, local);
+        if (active) run_pass<DedupPass2, MODE, sel_of_mode(MODE)>(src, a, local);
     } else {
         __syncthreads();
-        if (active) run_pass<FullPass0, MODE>(src, a, local);
+        if (active) run_pass<FullPass0, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
-        if (active) run_pass<FullPass1, MODE>(src, a, local);
+        if (active) run_pass<FullPass1, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
-        if (active) run_pass<FullPass2, MODE>(src, a, local);
+        if (active) run_pass<FullPass2, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
-        if (active) run_pass<FullPass3, MODE>(src, a, local);
+        if (active) run_pass<FullPass3, MODE, sel_of_mode(MODE)>(src, a, local);
     }
 }
 
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __gr
     if (local >= a.n) return;
     ValueSource src;
     src.row = values + local * T;  // `values` already points at this launch's first path
-    run_pass<IDS, MODE>(src, a, local);
+    run_pass<IDS, MODE, MCTS_SEL_REPLAY>(src, a, local);
 }
 
 template <int K, bool GLOBAL = false>

@@ -286,25 +286,106 @@ static __global__ void __launch_bounds__(128) k_shuffle_values(const __grid_cons
 
 // ---- exact-order reduction over the paths of one chunk --------------------------------------
 
-// grid (ceil(2^d / 64), 40): partial[arr][j] = raw pairwise sum of node j at depth d.  64-thread blocks with
-// <= 64 registers fit beside three resident k_sim_paths blocks (4096 registers are left per SM), so
-// the reduction of one chunk really overlaps the path kernel of the next.
-static __global__ void __launch_bounds__(64) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
+// grid (ceil(2^d / 8), 40), 64-thread blocks: partial[arr][j] = raw pairwise sum of node j at depth d, one
+// 8-lane group per node.  The eight lanes ARE the eight interleaved accumulators of NumPy's pairwise leaf
+// (lane j adds a[j], a[8+j], a[16+j], ...), so every load instruction of a group reads 64 contiguous bytes
+// (whole sectors, four groups per warp) and the leaf result ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a
+// three-step butterfly (fp addition commutes, the association is the tree's).  All lanes of a group walk
+// the node's sub-tree (a few leaves) in lock step.  64-thread blocks with <= 64 registers fit beside three
+// resident k_sim_paths blocks (4096 registers are left per SM), so the reduction of one chunk really
+// overlaps the path kernel of the next.
+__device__ __forceinline__ double group8_leaf_sum(const double *__restrict__ a, int64_t n, int lane, double &mn, double &mx)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int arr = blockIdx.y;
-    if (j >= ((int64_t)1 << d)) return;
-    int64_t start, len;
-    np_node_at_depth(n, d, j, &start, &len);
-    const double *a = out + (int64_t)arr * ld + start;
-    const double s = np_pairwise_raw(a, len);
-    double mn = a[0], mx = a[0];
-    for (int64_t i = 1; i < len; i++) {
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+    double res;
+    int64_t i = 0;
+    if (n >= 8) {
+        double r = a[lane];
+        mn = r < mn ? r : mn;
+        mx = r > mx ? r : mx;
+        for (i = 8; i < n - (n % 8); i += 8) {
+            const double v = a[i + lane];
+            r = r + v;
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+        }
+        r = r + __shfl_xor_sync(gmask, r, 1);
+        r = r + __shfl_xor_sync(gmask, r, 2);
+        res = r + __shfl_xor_sync(gmask, r, 4);
+    } else {
+        res = 0.;
+    }
+    for (; i < n; i++) {  // n % 8 tail (only the last leaf of an array has one), or the whole n < 8 case
         const double v = a[i];
+        res = res + v;
         mn = v < mn ? v : mn;
         mx = v > mx ? v : mx;
     }
-    part[(int64_t)arr * pstride + j] = s;
+    return res;
+}
+
+static __global__ void __launch_bounds__(64) k_reduce_nodes(const double *__restrict__ out, int64_t ld, int64_t n, int d, double *__restrict__ part, int64_t pstride)
+{
+    const int lane = threadIdx.x & 7;
+    const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 3);
+    const int arr = blockIdx.y;
+    if (j >= ((int64_t)1 << d)) return;  // whole groups leave together
+    int64_t start, len;
+    np_node_at_depth(n, d, j, &start, &len);
+    const double *a = out + (int64_t)arr * ld + start;
+    double mn = a[0], mx = a[0];
+    // post-order walk of the node's sub-tree (np_pairwise_raw with a cooperative leaf); depth <= 8 here
+    int64_t nn[12];
+    double left[12];
+    int8_t st[12];
+    int sp = 1;
+    int64_t pos = 0;
+    nn[0] = len;
+    st[0] = 0;
+    double v = 0.0;
+    bool done = false;
+    while (!done) {
+        const int top = sp - 1;
+        if (st[top] == 0) {
+            if (nn[top] <= 128) {
+                v = group8_leaf_sum(a + pos, nn[top], lane, mn, mx);
+                pos += nn[top];
+                sp--;
+            } else {
+                st[top] = 1;
+                nn[sp] = np_split_hd(nn[top]);
+                st[sp] = 0;
+                sp++;
+                continue;
+            }
+        }
+        while (true) {
+            if (sp == 0) {
+                done = true;
+                break;
+            }
+            const int par = sp - 1;
+            if (st[par] == 1) {
+                left[par] = v;
+                st[par] = 2;
+                nn[sp] = nn[par] - np_split_hd(nn[par]);
+                st[sp] = 0;
+                sp++;
+                break;
+            }
+            v = left[par] + v;
+            sp--;
+        }
+    }
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+        const double omn = __shfl_xor_sync(gmask, mn, s), omx = __shfl_xor_sync(gmask, mx, s);
+        mn = omn < mn ? omn : mn;
+        mx = omx > mx ? omx : mx;
+    }
+    if (lane != 0) return;
+    part[(int64_t)arr * pstride + j] = v;
     part[(int64_t)(40 + arr) * pstride + j] = mn;
     part[(int64_t)(80 + arr) * pstride + j] = mx;
 }

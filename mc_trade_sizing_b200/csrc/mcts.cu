@@ -493,7 +493,7 @@ static int launch_reduce(mcts_handle *h, Lane &L, int64_t n, int64_t first_path,
     if (rc) return rc;
     const int64_t pstride = L.cap_part / 160;
     if ((rc = mark(h, L.stream, h->ev_reduce, true))) return rc;
-    dim3 grid((unsigned)((nodes + 63) / 64), 40);
+    dim3 grid((unsigned)((nodes + 7) / 8), 40);  // one 8-lane group per node
     k_reduce_nodes<<<grid, 64, 0, L.stream>>>(L.d_out, L.cap_paths, n, d, L.d_part, pstride);
     CUDA_TRY(cudaGetLastError());
     k_reduce_top<<<40, 64, 0, L.stream>>>(L.d_part, pstride, d, d_rec, first_path, n);

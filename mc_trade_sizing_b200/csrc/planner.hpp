@@ -268,11 +268,15 @@ inline double combine_visit(int64_t n, int64_t chunk, const double *partials, in
 }
 
 // Depth of the perfect-binary top of the tree used by the device reduction of one chunk:
-// all nodes above depth d are internal (> 128 elements), nodes at depth d hold ~1024..2047.
+// all nodes above depth d are internal (> 128 elements), nodes at depth d hold ~kReduceNode..2*kReduceNode-1.
+#ifndef MCTS_REDUCE_NODE
+#define MCTS_REDUCE_NODE 1024
+#endif
+constexpr int64_t kReduceNode = MCTS_REDUCE_NODE;
 inline int reduce_depth(int64_t n)
 {
     int d = 0;
-    while ((n >> (d + 1)) >= 1024 && d < 20) d++;
+    while ((n >> (d + 1)) >= kReduceNode && d < 24) d++;
     return d;
 }
 

@@ -87,6 +87,23 @@ def test_replay_chunked_aggregates_match_numpy_order(eng):
             assert out["summary"][s, 0] == float(np.mean(out["profit"][s])), (chunk, s)
 
 
+def test_replay_staged_copy_many_slices_and_pinned_input(eng):
+    """96 MB of caller sequences: twelve 8 MB slices over the stager's worker threads (csrc/stager.hpp), three chunks
+    through the two device staging areas; then the same array from pinned memory (direct DMA, no staging)."""
+    import torch
+    rng = np.random.default_rng(11)
+    vals = rng.choice([204.60000000000002, 167.4, -240.9, 186.0, -219.0, 3.5], size=(60000, 200))
+    ref = oracle.eval_paths(vals)
+    out = eng.replay(vals, options=eng.options(chunk_paths=20000))
+    assert_bitexact(out["profit"], ref["profit"], "staged profit")
+    assert_bitexact(out["dd"], ref["dd"], "staged dd")
+    assert_bitexact(out["summary"], ref["summary"], "staged summary")
+    pinned = torch.from_numpy(vals).pin_memory()
+    out2 = eng.replay(pinned.numpy(), options=eng.options(chunk_paths=20000))
+    assert_bitexact(out2["profit"], ref["profit"], "pinned profit")
+    assert_bitexact(out2["summary"], ref["summary"], "pinned summary")
+
+
 def test_replay_int64_regime_arrays(eng, kat):
     """The reference's regime arrays are int64 (SURVEY 7.3 #10); fp64 on device is exact for them."""
     seqs = kat["a5_regime/seqs"]

@@ -168,6 +168,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # NCCL writes its version banner / debug log to stdout by default; stdout carries the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from mc_trade_sizing_b200 import Engine, make_params

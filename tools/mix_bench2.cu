@@ -1,3 +1,14 @@
+// mix_bench2.cu -- where can the two 64-bit conditional moves of a trade step (peak, drawdown) execute?
+// Register-only replica of the evaluator's step like mix_bench.cu, with the moves written as
+//   V=0   select pairs (what nvcc emits: FSEL x2 each, ALU pipe)                      <- the old kernel
+//   V=5/6/7  predicated add.f64 (ptxas lowers it to DADD + FSEL x2: more work, slower)
+//   V=8   sign mask + LOP3 (peak) ; V=9 integer sign test of u (peak)
+//   V=10-14  unpredicated integer arithmetic on a 0/1 mask, m*a + (1-m)*b (5 IMAD per move: slower)
+//   V=15/16/17  predicated IMAD with opaque multiplier 1 / addend 0 (both / peak only / drawdown only)  <- the shipped kernel
+//   V=18/19  predicated mad.wide (ptxas splits it into IMAD.WIDE + IADD3 + IMAD.X + SEL)
+// Results on the B200 are in profiles/r01_mix_bench2.txt; the replica itself is dispatch-bound (it carries ~3.5 register
+// moves per step that the real kernel does not have), so the decisive measurement was the real kernel.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/mix_bench2 tools/mix_bench2.cu && tools/mix_bench2
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -191,14 +202,19 @@ int main()
     cudaGetDeviceProperties(&p, 0);
     const int sms = p.multiProcessorCount;
     run<5, 0>(3, sms);
+    run<5, 5>(3, sms);
+    run<5, 6>(3, sms);
+    run<5, 7>(3, sms);
+    run<5, 8>(3, sms);
+    run<5, 9>(3, sms);
+    run<5, 10>(3, sms);
+    run<5, 13>(3, sms);
     run<5, 15>(3, sms);
     run<5, 16>(3, sms);
     run<5, 17>(3, sms);
     run<5, 18>(3, sms);
-    run<5, 19>(3, sms);
     run<5, 15>(2, sms);
     run<5, 15>(4, sms);
-    run<5, 18>(2, sms);
-    run<5, 18>(4, sms);
+    run<5, 0>(4, sms);
     return 0;
 }

@@ -92,7 +92,13 @@ class Stager {
         };
         std::vector<std::thread> th;
         th.reserve((size_t)n);
-        for (int i = 1; i < n; i++) th.emplace_back(work, i);
+        for (int i = 1; i < n; i++) {
+            try {
+                th.emplace_back(work, i);
+            } catch (...) {  // no more threads: this thread does the stripe itself (no C++ exception may cross the C ABI)
+                work(i);
+            }
+        }
         work(0);
         for (auto &t : th) t.join();
         for (int i = 0; i < n; i++) {

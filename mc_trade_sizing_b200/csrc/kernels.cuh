@@ -38,7 +38,7 @@ enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
 #define MCTS_SEL_FULL 3    // +4.4 %: the select version saturates the ALU pipe
 #endif
 #ifndef MCTS_SEL_DEDUP
-#define MCTS_SEL_DEDUP 0   // 4-strategy passes: predicated moves measured 10 % slower
+#define MCTS_SEL_DEDUP 3   // +8 % with the searched pass composition (10 % slower with the first one)
 #endif
 #ifndef MCTS_SEL_CURVES
 #define MCTS_SEL_CURVES 0  // HBM-bound

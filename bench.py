@@ -168,8 +168,10 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    # NCCL writes its version banner / debug log to stdout by default; stdout carries the ONE JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the ONE JSON line: anything native libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from mc_trade_sizing_b200 import Engine, make_params
@@ -238,14 +240,17 @@ def main():
     value = steps_per_step_global * args.steps / (dev_ms * 1e-3)
 
     # e2e: the public API a user calls (run_all_strategies / its sharded form), host buffers in and out
+    def e2e_step(seed):
+        if world == 1:
+            return tm.run_all_strategies(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, n_sims, NUM_SHUFFLES, seed=seed,
+                                         device=local_rank, chunk_paths=CHUNK_PATHS)
+        return mdist.run_all_strategies_sharded(eng, prm, seed, rank, world, chunk_paths=CHUNK_PATHS, device=device)
+    for w in range(args.warmup):   # the module-level engine of run_all_strategies allocates its device buffers on first use
+        e2e_step(8000 + w)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        if world == 1:
-            rows = tm.run_all_strategies(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, n_sims, NUM_SHUFFLES, seed=9000 + s,
-                                         device=local_rank, chunk_paths=CHUNK_PATHS)
-        else:
-            rows = mdist.run_all_strategies_sharded(eng, prm, 9000 + s, rank, world, chunk_paths=CHUNK_PATHS, device=device)
+        rows = e2e_step(9000 + s)
     barrier()
     e2e_wall = time.perf_counter() - t0
     t_e2e = (tm.get_engine(local_rank) if world == 1 else eng).timing()
@@ -383,6 +388,8 @@ def main():
     line.update(extras)
     if not args.no_cpu_baseline and n_gpus == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k in ("value", "unit", "cores", "kind", "sample")}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

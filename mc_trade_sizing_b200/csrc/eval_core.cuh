@@ -420,30 +420,46 @@ MCTS_HD void iadd(int32_t &E, int32_t v)
     E += v;
 #endif
 }
-MCTS_HD void iadd_if(int32_t &E, int32_t v, bool p)
+// E += v when bit `bit` of the history mask `mask` is set (clear, if NEG).  The bit test lives inside the
+// asm so that it stays ONE LOP3-to-predicate per (trade, mask) -- ptxas merges the identical tests of the
+// strategies that share it; handed over as a bool it became shift + and + compare per use.
+template <bool NEG>
+MCTS_HD void iadd_if(int32_t &E, int32_t v, uint32_t mask, uint32_t bit)
 {
 #if defined(__CUDA_ARCH__)
-    asm("{ .reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q mad.lo.s32 %0, %1, %2, %0; }" : "+r"(E) : "r"(v), "r"(c_int_one), "r"((uint32_t)p));
+    if constexpr (NEG)
+        asm("{ .reg .pred q; .reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.eq.u32 q, t, 0;\n\t@q mad.lo.s32 %0, %1, %2, %0; }"
+            : "+r"(E) : "r"(v), "r"(c_int_one), "r"(mask), "r"(bit));
+    else
+        asm("{ .reg .pred q; .reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\t@q mad.lo.s32 %0, %1, %2, %0; }"
+            : "+r"(E) : "r"(v), "r"(c_int_one), "r"(mask), "r"(bit));
 #else
-    if (p) E += v;
+    if (((mask & bit) != 0) != NEG) E += v;
 #endif
 }
 
-// E += size * v, size in {0, 1, 2, 3} by the behaviour's rule (cf. contribution<RULE>)
-template <int RULE>
-MCTS_HD void add_contribution_i(int32_t &E, const Preds &p, int32_t v1, int32_t v2)
+// E += size * v, size in {0, 1, 2, 3} by the behaviour's rule (cf. contribution<RULE>).  BINARY: from the
+// second block on "lost" is "did not win" (pl = !pw) and s16 = pll (make_masks_binary).
+template <int RULE, bool BINARY>
+MCTS_HD void add_contribution_i(int32_t &E, const Masks &m, uint32_t bit, int32_t v1, int32_t v2)
 {
     if constexpr (RULE == R_C1) iadd(E, v1);
-    if constexpr (RULE == R_AM) { iadd(E, v1); iadd_if(E, v1, p.pw); }
-    if constexpr (RULE == R_F1) { iadd(E, v1); iadd_if(E, v1, p.fw); }
-    if constexpr (RULE == R_MG) { iadd(E, v1); iadd_if(E, v1, p.pl); }
-    if constexpr (RULE == R_MG2) { iadd(E, v1); iadd_if(E, v1, p.pll); }
-    if constexpr (RULE == R_P1) iadd_if(E, v1, !p.pw);
-    if constexpr (RULE == R_P2) iadd_if(E, v1, !p.pww);
-    if constexpr (RULE == R_S16) { iadd_if(E, v1, !p.pw); iadd_if(E, v1, p.s16); }  // s16 implies !pw
-    if constexpr (RULE == R_S18) { iadd(E, v1); iadd_if(E, v2, p.pww); }
-    if constexpr (RULE == R_S19) { iadd(E, v1); iadd_if(E, v1, p.pww); iadd_if(E, v2, p.pll); }  // pww, pll exclusive
-    if constexpr (RULE == R_S20) { iadd(E, v1); iadd_if(E, v2, p.pll); }
+    if constexpr (RULE == R_AM) { iadd(E, v1); iadd_if<false>(E, v1, m.pw, bit); }
+    if constexpr (RULE == R_F1) { iadd(E, v1); iadd_if<false>(E, v1, m.fw, bit); }
+    if constexpr (RULE == R_MG) {
+        iadd(E, v1);
+        if constexpr (BINARY) iadd_if<true>(E, v1, m.pw, bit); else iadd_if<false>(E, v1, m.pl, bit);
+    }
+    if constexpr (RULE == R_MG2) { iadd(E, v1); iadd_if<false>(E, v1, m.pll, bit); }
+    if constexpr (RULE == R_P1) iadd_if<true>(E, v1, m.pw, bit);
+    if constexpr (RULE == R_P2) iadd_if<true>(E, v1, m.pww, bit);
+    if constexpr (RULE == R_S16) {  // s16 implies !pw
+        iadd_if<true>(E, v1, m.pw, bit);
+        iadd_if<false>(E, v1, BINARY ? m.pll : m.s16, bit);
+    }
+    if constexpr (RULE == R_S18) { iadd(E, v1); iadd_if<false>(E, v2, m.pww, bit); }
+    if constexpr (RULE == R_S19) { iadd(E, v1); iadd_if<false>(E, v1, m.pww, bit); iadd_if<false>(E, v2, m.pll, bit); }  // pww, pll exclusive
+    if constexpr (RULE == R_S20) { iadd(E, v1); iadd_if<false>(E, v2, m.pll, bit); }
 }
 
 MCTS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
@@ -478,11 +494,10 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
         static_for<8>([&](auto I) {
             constexpr int i = decltype(I)::value;
             const IntTab t = tab[(word >> (4 * i)) & 15u];
-            const Preds p = trade_preds<BINARY>(m, mask_bit(i));
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                add_contribution_i<rule>(E[s], p, t.v1, t.v2);
+                add_contribution_i<rule, BINARY>(E[s], m, mask_bit(i), t.v1, t.v2);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });
@@ -497,11 +512,10 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
         const Masks m = make_masks(W, W ^ valid, h);
         for (int i = 0; i < tail; i++) {
             const IntTab t = tab[(word >> (4 * i)) & 15u];
-            const Preds p = trade_preds<false>(m, mask_bit(i));
             static_for<NS>([&](auto S) {
                 constexpr int s = decltype(S)::value;
                 constexpr int rule = rule_of_id(IDS::id(s));
-                add_contribution_i<rule>(E[s], p, t.v1, t.v2);
+                add_contribution_i<rule, false>(E[s], m, mask_bit(i), t.v1, t.v2);
                 dd[s] = imin(dd[s], E[s] - peak[s]);
                 peak[s] = imax(peak[s], E[s]);
             });

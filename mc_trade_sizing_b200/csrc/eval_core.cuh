@@ -63,12 +63,13 @@ struct IdList {
 // they are written decides how well ptxas allocates the register pairs of the 8-trade loop body (12.5 to
 // 16 instructions per trade-step for the same five rules): the lists below are the best of an exhaustive
 // search over the orders of each pass and a hill climb over compositions, scored by the SASS instruction
-// count of the loop bodies and confirmed on the B200 (22.27 -> 21.74 ms per 2.1 M paths).
+// count of the loop bodies and confirmed on the B200 (22.27 -> 21.09 ms per 2.1 M paths together with
+// the head-select count of sel_of_mode, kernels.cuh).
 #ifndef MCTS_FP0
-#define MCTS_FP0 6, 9, 2, 1, 4
-#define MCTS_FP1 7, 10, 13, 3, 5
-#define MCTS_FP2 11, 18, 15, 14, 16
-#define MCTS_FP3 17, 12, 19, 20, 8
+#define MCTS_FP0 6, 9, 1, 2, 4
+#define MCTS_FP1 7, 10, 3, 13, 5
+#define MCTS_FP2 14, 11, 16, 15, 18
+#define MCTS_FP3 17, 12, 8, 19, 20
 #endif
 using FullPass0 = IdList<MCTS_FP0>;
 using FullPass1 = IdList<MCTS_FP1>;
@@ -306,7 +307,10 @@ MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
             const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
-            trade_step<SEL>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
+            // ptxas turns the predicated moves of the first trades of a loop body into copy + select (the state
+            // crosses the back edge); plain selects cost the same there and need no copies
+            // (SEL >> 2 = how many leading trades of the block use plain selects)
+            trade_step<(i < (SEL >> 2) ? 0 : (SEL & 3))>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     });
@@ -326,7 +330,7 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
             const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
-            trade_step<SEL>(a.E[s], a.peak[s], a.dd[s], res[s], c);
+            trade_step<(SEL & 3)>(a.E[s], a.peak[s], a.dd[s], res[s], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     }

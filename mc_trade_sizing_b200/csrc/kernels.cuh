@@ -33,9 +33,11 @@ constexpr int kTabWords = 16 * sizeof(Tab) / 4;
 enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
 
 // How peak / drawdown are updated in each kernel flavour (eval_core.cuh trade_step<SEL>): predicated
-// IMAD moves on the FMA pipe (3) where that measured faster on the B200, select pairs (0) elsewhere.
+// IMAD moves on the FMA pipe (3) where that measured faster on the B200, select pairs (0) elsewhere;
+// + 4 * (number of leading trades of every 8-trade block that keep the select pairs).
 #ifndef MCTS_SEL_FULL
-#define MCTS_SEL_FULL 3    // +4.4 %: the select version saturates the ALU pipe
+#define MCTS_SEL_FULL 7    // predicated moves (+4.4 %: the select version saturates the ALU pipe), first trade of a block: selects
+                           // (k_sim_paths per 2.1 M paths, each with its own searched pass orders: 0 -> 21.72 ms, 1 -> 21.09, 2 -> 21.49, 3 -> 21.68)
 #endif
 #ifndef MCTS_SEL_DEDUP
 #define MCTS_SEL_DEDUP 3   // +8 % with the searched pass composition (10 % slower with the first one)

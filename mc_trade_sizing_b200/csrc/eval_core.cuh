@@ -76,11 +76,11 @@ using FullPass1 = IdList<MCTS_FP1>;
 using FullPass2 = IdList<MCTS_FP2>;
 using FullPass3 = IdList<MCTS_FP3>;
 // one representative per behaviour class (results fanned out by the caller); composition and order from
-// the same search (with predicated moves: 14.65 -> 13.59 ms per 2.1 M paths)
+// the same search (with predicated moves and one head select: 14.65 -> 13.37 ms per 2.1 M paths)
 #ifndef MCTS_DP0
-#define MCTS_DP0 9, 6, 2
-#define MCTS_DP1 8, 1, 11, 16
-#define MCTS_DP2 20, 18, 4, 19
+#define MCTS_DP0 18, 4, 1
+#define MCTS_DP1 9, 8, 16, 6
+#define MCTS_DP2 11, 20, 2, 19
 #endif
 using DedupPass0 = IdList<MCTS_DP0>;
 using DedupPass1 = IdList<MCTS_DP1>;

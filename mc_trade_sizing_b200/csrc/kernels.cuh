@@ -40,7 +40,7 @@ enum PathMode : int { PM_FULL = 0, PM_DEDUP = 1, PM_CURVES = 2 };
                            // (k_sim_paths per 2.1 M paths, each with its own searched pass orders: 0 -> 21.72 ms, 1 -> 21.09, 2 -> 21.49, 3 -> 21.68)
 #endif
 #ifndef MCTS_SEL_DEDUP
-#define MCTS_SEL_DEDUP 3   // +8 % with the searched pass composition (10 % slower with the first one)
+#define MCTS_SEL_DEDUP 7   // +10 % with the searched pass composition (10 % slower with the first one)
 #endif
 #ifndef MCTS_SEL_CURVES
 #define MCTS_SEL_CURVES 0  // HBM-bound

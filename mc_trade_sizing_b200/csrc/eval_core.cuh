@@ -17,6 +17,7 @@
 // No multiply-add contraction can occur here: the categorical path only adds (products v*1, v*2,
 // v*3 are tabulated on the host), the replay path uses __dmul_rn.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include <type_traits>
@@ -85,6 +86,45 @@ using FullPass3 = IdList<MCTS_FP3>;
 using DedupPass0 = IdList<MCTS_DP0>;
 using DedupPass1 = IdList<MCTS_DP1>;
 using DedupPass2 = IdList<MCTS_DP2>;
+
+// the pass lists are macros (searched, see above): check them where they are defined
+template <class P>
+constexpr int count_id(int id)
+{
+    int n = 0;
+    for (int i = 0; i < P::N; i++) n += P::id(i) == id ? 1 : 0;
+    return n;
+}
+template <class P>
+constexpr int count_rule(int rule)
+{
+    int n = 0;
+    for (int i = 0; i < P::N; i++) n += rule_of_id(P::id(i)) == rule ? 1 : 0;
+    return n;
+}
+template <class P>
+constexpr bool rules_distinct()
+{
+    for (int r = R_C1; r <= R_S20; r++)
+        if (count_rule<P>(r) > 1) return false;
+    return true;
+}
+constexpr bool full_passes_cover_all_ids()
+{
+    for (int id = 1; id <= 20; id++)
+        if (count_id<FullPass0>(id) + count_id<FullPass1>(id) + count_id<FullPass2>(id) + count_id<FullPass3>(id) != 1) return false;
+    return true;
+}
+constexpr bool dedup_passes_cover_all_rules()
+{
+    for (int r = R_C1; r <= R_S20; r++)
+        if (count_rule<DedupPass0>(r) + count_rule<DedupPass1>(r) + count_rule<DedupPass2>(r) != 1) return false;
+    return true;
+}
+static_assert(full_passes_cover_all_ids(), "every strategy id must appear in exactly one full pass");
+static_assert(rules_distinct<FullPass0>() && rules_distinct<FullPass1>() && rules_distinct<FullPass2>() && rules_distinct<FullPass3>(),
+              "two ids of one behaviour class in one pass would be merged by the compiler");
+static_assert(dedup_passes_cover_all_rules(), "every behaviour class must appear in exactly one dedup pass");
 
 template <int N, class F, int... Is>
 MCTS_HD void static_for_impl(F &&f, std::integer_sequence<int, Is...>)

@@ -32,7 +32,7 @@ CHUNK_PATHS = 1 << 22          # the library default: two 4.19 M-path chunks per
 METRIC = "trade-steps/sec (paths x trades x strategies)"
 UNIT = "trade-steps/s"
 FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)
-TRAFFIC_PER_LAUNCH = 641.9e6         # dram bytes read + written by one k_sim_paths launch (ncu --set full, profiles/)
+TRAFFIC_PER_LAUNCH = 642.2e6         # dram bytes read + written by one k_sim_paths launch (ncu --set full, profiles/)
 
 
 def workload_config(n_gpus):

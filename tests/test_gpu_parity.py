@@ -422,6 +422,24 @@ def test_run_all_strategies_drop_in(eng):
         assert_bitexact(np.array(by_desc[DESCRIPTIONS[i + 1]]), ref[i], "row %d" % (i + 1))
 
 
+def test_three_concurrent_cli_processes_share_the_gpu():
+    """dps.py runs three CLI subprocesses at a time (dps.py:268): each creates its own handle and CUDA context on the
+    same device; all must succeed and, with the same seed, print the same table."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "src", "trading_models.py"), "--hit_rate", "0.82", "--avg_win", "186", "--avg_loss", "219",
+           "--num_simulations", "200", "--num_trades", "1000", "--num_mc_shuffles", "20"]
+    env = dict(os.environ, MCTS_SEED="77")
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for _ in range(3)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-2000:]
+        assert out.count("\n") > 25
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+
+
 def test_dps_sweep_in_one_process(eng):
     """N2: the 12 runs of dps.py in one process; every block parses with dps.py's row regex (dps.py:356)."""
     import re

@@ -370,6 +370,39 @@ def test_full_size_regime_config_c4(eng):
     assert ref["agg"][0].count == 10**7
 
 
+def test_scale_sweep_config_c5_slice(eng):
+    """Config C5 (1e9 'No Markov' paths over 1/2/4/8 GPUs) on a 2e7-path slice: non-integer values, so the mean depends on
+    the summation order.  Size-independent properties: the aggregates are bit-identical for the library-default chunking,
+    for 2 / 3 / 8 emulated ranks (disjoint chunk ranges combined on the host) and for the dedup evaluator; tie groups;
+    the analytic mean of strategy 1."""
+    n_sims, n_sh = 1_000_000, 20
+    prm = make_params(0.82, 186.0, 219.0, 1000, n_sims, n_sh)
+    P = n_sims * n_sh
+    ref = eng.simulate(prm, seed=5)
+    s = ref["summary"]
+    assert_bitexact(eng.simulate(prm, seed=5, options=eng.options(dedup=True))["summary"], s, "dedup")
+    first, count = Engine.plan(P, 0)
+    n = len(first)
+    assert n >= 8
+    for G in (2, 3, 8):
+        recs = (_ffi.ChunkResult * n)()
+        bounds = [n * g // G for g in range(G + 1)]
+        for g in range(G):
+            part, m = eng.simulate_chunks(prm, 5, bounds[g], bounds[g + 1])
+            for i in range(m):
+                C.memmove(C.byref(recs[bounds[g] + i]), C.byref(part[i]), C.sizeof(_ffi.ChunkResult))
+        agg = Engine.combine(P, 0, recs, n)
+        for k in range(20):
+            for f, _ in _ffi.Agg._fields_:
+                a, b = getattr(agg[k], f), getattr(ref["agg"][k], f)
+                assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64), (G, k, f)
+    for g in TIE_GROUPS:
+        for other in g[1:]:
+            assert_bitexact(s[g[0] - 1], s[other - 1], "tie group %s" % (g,))
+    assert abs(s[0, 0] - 103063.2) < 5 * 6300 / np.sqrt(n_sims)      # sd of a simulation's strategy-1 profit ~6300
+    assert ref["agg"][0].count == P
+
+
 def test_curve_export_matches_reference_equity_curves(eng):
     """Extension K4: exported curves == np.cumsum of each strategy's contributions on the device-generated
     sequences (the temporary of :167), bit for bit; layout [20][ceil(L/2)][n][2]."""

@@ -37,7 +37,7 @@ extern "C" {
 
 #define MCTS_NSTRAT 20
 #define MCTS_MAX_REGIMES 16
-#define MCTS_ABI_VERSION 1
+#define MCTS_ABI_VERSION 2
 
 typedef enum {
     MCTS_OK = 0,
@@ -172,6 +172,38 @@ int mcts_simulate_chunks(mcts_handle *h, const mcts_params *p, uint64_t seed, co
  * in NumPy's tree order.  Pure host arithmetic on ~1 KB records. */
 int mcts_combine(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks,
                  mcts_agg *agg);
+
+/* Chunk size used when the caller gives none and the plan is to be split over `n_shards` devices / ranks:
+ * every shard gets at least four chunks whenever there are enough paths (>= 16,384 per chunk), never more than
+ * the single-device default of 1<<22.  Results do not depend on the chunk size. */
+int64_t mcts_auto_chunk(int64_t P, int n_shards);
+/* Contiguous runs of chunks with (nearly) equal path counts: shard d evaluates chunks
+ * [bounds[d], bounds[d+1]) of the plan for (P, chunk_paths); bounds has n_shards + 1 entries. */
+int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *bounds);
+
+/* --- several devices behind one call (the only caller, main() at :588-601, stays unchanged) ------- */
+
+/* A group drives several B200s of one box from ONE process: the chunk plan is cut into contiguous runs
+ * of (nearly) equal path counts, one host thread per device evaluates its run on that device's handle
+ * (Philox draws are keyed by (simulation, shuffle, trade), so a device regenerates whatever it needs),
+ * and the ~1 KB chunk records are folded on the host in tree order: the result is bit-identical to
+ * mcts_simulate on one device for any number of devices.  There is no device-to-device exchange at all
+ * (paths are independent), so no collective is involved; the torch.distributed form of the same thing
+ * (one process per GPU, one all_gather of the records) lives in mc_trade_sizing_b200/distributed.py. */
+typedef struct mcts_group mcts_group;
+
+/* devices == NULL or n <= 0: every visible compute-capability-10.x device.  Fails with MCTS_ENODEVICE
+ * if there is none. */
+int mcts_group_create(const int *devices, int n, mcts_group **out);
+void mcts_group_destroy(mcts_group *g);
+int mcts_group_size(const mcts_group *g);
+/* CUDA device index of member i (or -1). */
+int mcts_group_device(const mcts_group *g, int i);
+/* Same contract as mcts_simulate.  opt->chunk_paths == 0 means mcts_auto_chunk(P, group size). */
+int mcts_group_simulate(mcts_group *g, const mcts_params *p, uint64_t seed, const mcts_options *opt,
+                        mcts_agg *agg, double *profit, double *dd);
+/* Per-device timing of the last mcts_group_simulate: out[mcts_group_size(g)]. */
+int mcts_group_get_timing(const mcts_group *g, mcts_timing *out);
 
 /* --- equity-curve export (extension; the reference only has the temporary of :167) -------- */
 

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MCTS_LIB") or os.path.join(HERE, "libmcts.so")
 
 NSTRAT = 20
 MAX_REGIMES = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODE_DYNAMIC, MODE_MARKOV1, MODE_MARKOV2, MODE_REGIME = 0, 1, 2, 3
 
@@ -78,6 +78,14 @@ PROTOTYPES = [
     ("mcts_simulate_chunks", C.c_int, [C.c_void_p, C.POINTER(Params), C.c_uint64, C.POINTER(Options), C.c_int64, C.c_int64,
                                        C.POINTER(ChunkResult)]),
     ("mcts_combine", C.c_int, [C.c_int64, C.c_int64, C.POINTER(ChunkResult), C.c_int64, C.POINTER(Agg)]),
+    ("mcts_auto_chunk", C.c_int64, [C.c_int64, C.c_int]),
+    ("mcts_plan_shards", C.c_int, [C.c_int64, C.c_int64, C.c_int, _i64p]),
+    ("mcts_group_create", C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    ("mcts_group_destroy", None, [C.c_void_p]),
+    ("mcts_group_size", C.c_int, [C.c_void_p]),
+    ("mcts_group_device", C.c_int, [C.c_void_p, C.c_int]),
+    ("mcts_group_simulate", C.c_int, [C.c_void_p, C.POINTER(Params), C.c_uint64, C.POINTER(Options), C.POINTER(Agg), _dp, _dp]),
+    ("mcts_group_get_timing", C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     ("mcts_export_curves", C.c_int, [C.c_void_p, C.POINTER(Params), C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),
     ("mcts_device_alloc", C.c_void_p, [C.c_void_p, C.c_int64]),
     ("mcts_device_free", None, [C.c_void_p, C.c_void_p]),

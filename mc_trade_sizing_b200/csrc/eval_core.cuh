@@ -59,18 +59,20 @@ struct IdList {
     }
 };
 
-// all 20 state machines, five per pass; no two ids of one behaviour class share a pass, so every
-// id carries its own equity / peak / drawdown / profit chain.  Which ids share a pass and in which order
-// they are written decides how well ptxas allocates the register pairs of the 8-trade loop body (12.5 to
-// 16 instructions per trade-step for the same five rules): the lists below are the best of an exhaustive
-// search over the orders of each pass and a hill climb over compositions, scored by the SASS instruction
-// count of the loop bodies and confirmed on the B200 (22.27 -> 21.09 ms per 2.1 M paths together with
-// the head-select count of sel_of_mode, kernels.cuh).
+// all 20 state machines, five per pass.  Ids of one behaviour class SHARE a pass: their
+// contribution -- the select among {0, v, 2v, fl(3v)} and its predicate test -- is computed once per trade
+// and feeds every id of the class, while each id keeps its own equity / peak / drawdown / profit chain
+// (20 chains in all).  The chains of one class would be provably identical, so the device code starts every
+// chain from a value read from constant memory (c_chain_start, -0.0 at run time) that the compiler cannot see
+// through: nothing is merged, all 20 state machines are carried to the end.  Which classes share a pass and
+// the order the ids are written in decides how well ptxas allocates the register pairs of the 8-trade loop
+// body: the lists below are the best of a search (tools/pass_search) scored by the SASS instruction count of
+// the loop bodies and confirmed on the B200.
 #ifndef MCTS_FP0
-#define MCTS_FP0 6, 9, 1, 2, 4
-#define MCTS_FP1 7, 10, 3, 13, 5
-#define MCTS_FP2 14, 11, 16, 15, 18
-#define MCTS_FP3 17, 12, 8, 19, 20
+#define MCTS_FP0 4, 5, 14, 17, 8
+#define MCTS_FP1 9, 10, 15, 11, 12
+#define MCTS_FP2 1, 3, 2, 13, 16
+#define MCTS_FP3 6, 7, 18, 19, 20
 #endif
 using FullPass0 = IdList<MCTS_FP0>;
 using FullPass1 = IdList<MCTS_FP1>;
@@ -122,8 +124,7 @@ constexpr bool dedup_passes_cover_all_rules()
     return true;
 }
 static_assert(full_passes_cover_all_ids(), "every strategy id must appear in exactly one full pass");
-static_assert(rules_distinct<FullPass0>() && rules_distinct<FullPass1>() && rules_distinct<FullPass2>() && rules_distinct<FullPass3>(),
-              "two ids of one behaviour class in one pass would be merged by the compiler");
+static_assert(rules_distinct<DedupPass0>() && rules_distinct<DedupPass1>() && rules_distinct<DedupPass2>(), "dedup passes hold one id per behaviour class");
 static_assert(dedup_passes_cover_all_rules(), "every behaviour class must appear in exactly one dedup pass");
 
 template <int N, class F, int... Is>
@@ -253,17 +254,45 @@ struct Acc {
     History h;
 };
 
-template <int NS>
-MCTS_HD void acc_init(Acc<NS> &a)
+#if defined(__CUDACC__)
+// Start value (-0.0) of every id's chains, read from constant memory so that the compiler cannot prove two
+// chains of one behaviour class equal and merge them (cf. c_int_zero of the int32 evaluator).
+static __constant__ double c_chain_start[kNumStrategies + 1] = {-0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0,
+                                                                -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0, -0.0};
+#endif
+
+// -0.0 for chain `id`: a literal, or (OPAQUE, device only) the constant-memory copy
+template <bool OPAQUE>
+MCTS_HD double chain_start(int id)
+{
+#if defined(__CUDA_ARCH__)
+    if constexpr (OPAQUE) return c_chain_start[id];
+#endif
+    (void)id;
+    return neg_zero();
+}
+
+template <class IDS, bool OPAQUE>
+MCTS_HD void acc_reset_leaf(Acc<IDS::N> &a)
 {
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
-        a.E[s] = neg_zero();  // -0.0 + c == c bit for bit, so E_0 = c_0 needs no special case
+    for (int s = 0; s < IDS::N; s++) {
+        const double z = chain_start<OPAQUE>(IDS::id(s));  // leaf starts with r[j] = a[j]
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.r[s][j] = z;
+    }
+}
+
+template <class IDS, bool OPAQUE>
+MCTS_HD void acc_init(Acc<IDS::N> &a)
+{
+#pragma unroll
+    for (int s = 0; s < IDS::N; s++) {
+        a.E[s] = chain_start<OPAQUE>(IDS::id(s));  // -0.0 + c == c bit for bit, so E_0 = c_0 needs no special case
         a.peak[s] = neg_inf();  // first trade: u = +inf > 0 -> peak_0 = E_0, d_0 = +0.0
         a.dd[s] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) a.r[s][j] = neg_zero();  // leaf starts with r[j] = a[j]
     }
+    acc_reset_leaf<IDS, OPAQUE>(a);
     a.h.w = 0;
     a.h.l = 0;
 }
@@ -368,12 +397,13 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
 //   SRC: uint32_t load(int oct)       -> win bits of block `oct` (and latches its values)
 //        uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
 //        get<i>() / get_dyn(i)
-template <class IDS, int SEL = 0, class SRC, class SINK>
+//   OPAQUE: every id's chains start from constant memory (ids of one class in one pass stay separate chains)
+template <class IDS, int SEL = 0, bool OPAQUE = false, class SRC, class SINK>
 MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, double (&profit)[IDS::N], double (&drawdown)[IDS::N])
 {
     constexpr int NS = IDS::N;
     Acc<NS> a;
-    acc_init(a);
+    acc_init<IDS, OPAQUE>(a);
     double stk[NS][kMaxStackDepth];
     double res[NS];
     int sp = 0;
@@ -396,9 +426,8 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
         for (int s = 0; s < NS; s++) {
             // leaf result: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); a leaf without a full block starts from 0.
             res[s] = has_blocks ? ((a.r[s][0] + a.r[s][1]) + (a.r[s][2] + a.r[s][3])) + ((a.r[s][4] + a.r[s][5]) + (a.r[s][6] + a.r[s][7])) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) a.r[s][j] = neg_zero();
         }
+        acc_reset_leaf<IDS, OPAQUE>(a);
         if (leaf == n_leaves - 1 && sch->tail > 0) {
             uint32_t Lb;
             const uint32_t W = src.load_tail(oct, sch->tail, &Lb);
@@ -562,12 +591,34 @@ MCTS_HD void eval_path_int(const uint32_t *codes, int stride, const IntTab *tab,
 
 // ---- value sources ----------------------------------------------------------------------------
 
+// The value table as the kernels keep it in shared memory: three arrays with 8-byte stride, so the 16
+// entries of each span exactly the 32 banks once -- lanes reading different codes never conflict, lanes
+// reading the same code broadcast.  (The array-of-structs Tab of spec.hpp has a 32-byte stride: codes k and
+// k + 4 alias, 1.1e9 bank conflicts per launch in the round-1 profile.)
+struct TabSoA {
+    double v1[16], v2[16], v3[16];
+};
+MCTS_HD void tab_get(const Tab *tab, uint32_t code, double &v1, double &v2, double &v3)
+{
+    const Tab &t = tab[code];
+    v1 = t.v1;
+    v2 = t.v2;
+    v3 = t.v3;
+}
+MCTS_HD void tab_get(const TabSoA *tab, uint32_t code, double &v1, double &v2, double &v3)
+{
+    v1 = tab->v1[code];
+    v2 = tab->v2[code];
+    v3 = tab->v3[code];
+}
+
 // categorical: 8 trades per 32-bit word, 4-bit code each; code -> {v, 2v, fl(3v)} table
-struct CodeSource {
+template <class TAB>
+struct CodeSourceT {
     static constexpr bool kSharedLo = true;  // build_spec rejects subnormal / overflowing values
     const uint32_t *codes;  // word of block `oct` at codes[oct * stride]
     int stride;
-    const Tab *tab;
+    const TAB *tab;
     uint32_t word;
     MCTS_HD uint32_t load(int oct)
     {
@@ -585,19 +636,15 @@ struct CodeSource {
     template <int I>
     MCTS_HD void get(double &v1, double &v2, double &v3) const
     {
-        const Tab &t = tab[(word >> (4 * I)) & 15u];
-        v1 = t.v1;
-        v2 = t.v2;
-        v3 = t.v3;
+        tab_get(tab, (word >> (4 * I)) & 15u, v1, v2, v3);
     }
     MCTS_HD void get_dyn(int i, double &v1, double &v2, double &v3) const
     {
-        const Tab &t = tab[(word >> (4 * i)) & 15u];
-        v1 = t.v1;
-        v2 = t.v2;
-        v3 = t.v3;
+        tab_get(tab, (word >> (4 * i)) & 15u, v1, v2, v3);
     }
 };
+using CodeSource = CodeSourceT<Tab>;        // host harness: GenSpec::tab as it is
+using CodeSourceSoA = CodeSourceT<TabSoA>;  // kernels: shared-memory copy
 
 MCTS_HD double mul_rn(double a, double b)
 {

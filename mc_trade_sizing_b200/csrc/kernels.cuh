@@ -113,10 +113,10 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
         sink.local = local;
         sink.L = a.g.L;
         sink.half = (a.g.L + 1) >> 1;
-        eval_path<IDS, SEL>(src, sink, a.sched, profit, dd);
+        eval_path<IDS, SEL, false>(src, sink, a.sched, profit, dd);
     } else {
         NoSink sink;
-        eval_path<IDS, SEL>(src, sink, a.sched, profit, dd);
+        eval_path<IDS, SEL, MODE == PM_FULL>(src, sink, a.sched, profit, dd);  // PM_FULL: 20 separate chains
     }
     if (a.out == nullptr) return;
     static_for<IDS::N>([&](auto S) {
@@ -165,17 +165,21 @@ template <int K, int MODE, int BLOCK, bool GLOBAL = false>
 __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(const __grid_constant__ PathArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    Tab *tab = reinterpret_cast<Tab *>(smem);
+    TabSoA *tab = reinterpret_cast<TabSoA *>(smem);
     const int tid = threadIdx.x;
     uint32_t *codes = GLOBAL ? a.scratch + (size_t)blockIdx.x * BLOCK : smem + kTabWords;
     const int cstride = GLOBAL ? a.scratch_stride : BLOCK;
-    for (int i = tid; i < 16 * 4; i += BLOCK) reinterpret_cast<double *>(tab)[i] = reinterpret_cast<const double *>(a.g.tab)[i];
+    if (tid < 16) {
+        tab->v1[tid] = a.g.tab[tid].v1;
+        tab->v2[tid] = a.g.tab[tid].v2;
+        tab->v3[tid] = a.g.tab[tid].v3;
+    }
     __syncthreads();
     const int64_t local = (int64_t)blockIdx.x * BLOCK + tid;
     const bool active = local < a.n;
     // the code column of a thread is private: the barriers below are for phase alignment only
     if (active) generate_codes<K>(a, local, codes + tid, cstride);
-    CodeSource src;
+    CodeSourceSoA src;
     src.codes = codes + tid;
     src.stride = cstride;
     src.tab = tab;

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mcts.h"
@@ -158,6 +159,21 @@ static int ensure(T **ptr, int64_t *cap, int64_t need, size_t elem = sizeof(T))
     return MCTS_OK;
 }
 
+// streams, events and the leaf-schedule buffer of a fresh handle (mcts_create destroys the handle if this fails)
+static int init_handle(mcts_handle *h)
+{
+    for (auto &L : h->lane) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    }
+    h->stream = h->lane[0].stream;
+    CUDA_TRY(cudaEventCreate(&h->ev_begin));
+    CUDA_TRY(cudaEventCreate(&h->ev_end));
+    CUDA_TRY(cudaMalloc(&h->d_sched, sizeof(LeafSched)));
+    memset(&h->timing, 0, sizeof h->timing);
+    return MCTS_OK;
+}
+
 extern "C" {
 
 int mcts_abi_version(void) { return MCTS_ABI_VERSION; }
@@ -187,15 +203,11 @@ int mcts_create(int device, mcts_handle **out)
     if (!h) return fail(MCTS_ENOMEM, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    for (auto &L : h->lane) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    const int rc = init_handle(h);
+    if (rc) {  // g_err already holds the message; release whatever was created
+        mcts_destroy(h);
+        return rc;
     }
-    h->stream = h->lane[0].stream;
-    CUDA_TRY(cudaEventCreate(&h->ev_begin));
-    CUDA_TRY(cudaEventCreate(&h->ev_end));
-    CUDA_TRY(cudaMalloc(&h->d_sched, sizeof(LeafSched)));
-    memset(&h->timing, 0, sizeof h->timing);
     *out = h;
     return MCTS_OK;
 }
@@ -564,32 +576,43 @@ static int simulate_range(mcts_handle *h, const mcts_params *p, uint64_t seed, c
         if ((rc = ensure_out(h->lane[l], max_n))) return rc;
     if ((rc = ensure(&h->d_recs, &h->cap_recs, ce - cb))) return rc;
     if ((rc = fork_lanes(h))) return rc;
-    for (int64_t c = cb; c < ce; c++) {
-        Lane &L = h->lane[(c - cb) % n_lanes];
-        const int64_t f = first[c], n = count[c];
-        const int64_t s_lo = f / p->num_mc_shuffles, s_hi = (f + n - 1) / p->num_mc_shuffles;
-        if ((rc = launch_gen_base(h, L, g, seed, s_lo, s_hi - s_lo + 1))) return rc;
-        PathArgs a;
-        memset(&a, 0, sizeof a);
-        a.g = g;
-        a.seed = seed;
-        a.path0 = f;
-        a.n = n;
-        a.sim0 = s_lo;
-        a.n_sh = p->num_mc_shuffles;
-        a.counts = L.d_counts;
-        a.sched = h->d_sched;
-        a.out = L.d_out;
-        a.ld = L.cap_paths;
-        if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
-        rc = g.wide ? launch_wide(h, L, mode, a) : launch_paths(h, L, mode, a);
-        if (rc) return rc;
-        if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
-        if ((rc = launch_reduce(h, L, n, f, h->d_recs + (c - cb)))) return rc;
-        if ((rc = copy_paths_out(h, L, f, n, P, profit, dd))) return rc;
-        h->timing.trade_steps += n * (int64_t)g.L * MCTS_NSTRAT;
+    auto enqueue_chunks = [&]() -> int {
+        for (int64_t c = cb; c < ce; c++) {
+            Lane &L = h->lane[(c - cb) % n_lanes];
+            const int64_t f = first[c], n = count[c];
+            const int64_t s_lo = f / p->num_mc_shuffles, s_hi = (f + n - 1) / p->num_mc_shuffles;
+            int r = launch_gen_base(h, L, g, seed, s_lo, s_hi - s_lo + 1);
+            if (r) return r;
+            PathArgs a;
+            memset(&a, 0, sizeof a);
+            a.g = g;
+            a.seed = seed;
+            a.path0 = f;
+            a.n = n;
+            a.sim0 = s_lo;
+            a.n_sh = p->num_mc_shuffles;
+            a.counts = L.d_counts;
+            a.sched = h->d_sched;
+            a.out = L.d_out;
+            a.ld = L.cap_paths;
+            if ((r = mark(h, L.stream, h->ev_paths, true))) return r;
+            r = g.wide ? launch_wide(h, L, mode, a) : launch_paths(h, L, mode, a);
+            if (r) return r;
+            if ((r = mark(h, L.stream, h->ev_paths, false))) return r;
+            if ((r = launch_reduce(h, L, n, f, h->d_recs + (c - cb)))) return r;
+            if ((r = copy_paths_out(h, L, f, n, P, profit, dd))) return r;
+            h->timing.trade_steps += n * (int64_t)g.L * MCTS_NSTRAT;
+        }
+        return join_lanes(h);
+    };
+    if ((rc = enqueue_chunks())) {
+        // nothing may stay in flight on either lane (the caller's output buffers, the next call's events)
+        const std::string msg = g_err;
+        for (auto &L : h->lane) cudaStreamSynchronize(L.stream);
+        cudaGetLastError();
+        timing_reset(h);
+        return fail(rc, msg);
     }
-    if ((rc = join_lanes(h))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, h->d_recs, sizeof(mcts_chunk_result) * (size_t)(ce - cb), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * (ce - cb);
@@ -867,6 +890,145 @@ int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst
     cudaFree(d_clk);
     h->timing.launches = 6;
     return MCTS_OK;
+}
+
+
+// ---- several devices behind one call ----------------------------------------------------------
+
+struct mcts_group {
+    std::vector<mcts_handle *> dev;
+    std::vector<mcts_timing> timing;
+};
+
+int64_t mcts_auto_chunk(int64_t P, int n_shards)
+{
+    if (n_shards <= 1) return clamp_chunk(0);
+    int64_t c = P / (4 * (int64_t)n_shards);  // >= 4 chunks per shard: two per stream lane, and runs balance to within ~10 %
+    c = std::max<int64_t>(c, 16384);  // below this a launch no longer fills one GPU
+    return clamp_chunk(std::min<int64_t>(c, (int64_t)1 << 22));
+}
+
+int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *bounds)
+{
+    if (P <= 0) return fail(MCTS_EEMPTY, "no paths");
+    if (n_shards <= 0 || !bounds) return fail(MCTS_EINVAL, "mcts_plan_shards: bad arguments");
+    std::vector<int64_t> first, count;
+    plan_visit(0, P, clamp_chunk(chunk_paths), &first, &count);
+    for (int d = 0; d <= n_shards; d++) bounds[d] = (int64_t)count.size();
+    bounds[0] = 0;
+    int64_t acc = 0;
+    int d = 1;
+    for (size_t i = 0; i < count.size() && d < n_shards; i++) {
+        // chunk i belongs to the shard whose quantile of the path range holds the chunk's midpoint
+        while (d < n_shards && (acc + count[i] / 2) * n_shards >= P * d) bounds[d++] = (int64_t)i;
+        acc += count[i];
+    }
+    return MCTS_OK;
+}
+
+int mcts_group_create(const int *devices, int n, mcts_group **out)
+{
+    if (!out) return fail(MCTS_EINVAL, "mcts_group_create: out is NULL");
+    *out = nullptr;
+    std::vector<int> ids;
+    if (!devices || n <= 0) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0) {
+            cudaGetLastError();
+            return fail(MCTS_ENODEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libmcts has no CPU fallback");
+        }
+        for (int d = 0; d < count; d++) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ids.push_back(d);
+        }
+        if (ids.empty()) return fail(MCTS_ENODEVICE, "no compute-capability-10.x device visible; libmcts is built for sm_100a only");
+    } else {
+        ids.assign(devices, devices + n);
+        for (size_t i = 0; i < ids.size(); i++)
+            for (size_t j = 0; j < i; j++)
+                if (ids[i] == ids[j]) return fail(MCTS_EINVAL, "mcts_group_create: a device is listed twice");
+    }
+    mcts_group *g = new (std::nothrow) mcts_group();
+    if (!g) return fail(MCTS_ENOMEM, "out of host memory");
+    for (int d : ids) {
+        mcts_handle *h = nullptr;
+        const int rc = mcts_create(d, &h);
+        if (rc) {
+            mcts_group_destroy(g);
+            return rc;
+        }
+        g->dev.push_back(h);
+    }
+    g->timing.assign(g->dev.size(), mcts_timing());
+    *out = g;
+    return MCTS_OK;
+}
+
+void mcts_group_destroy(mcts_group *g)
+{
+    if (!g) return;
+    for (mcts_handle *h : g->dev) mcts_destroy(h);
+    delete g;
+}
+
+int mcts_group_size(const mcts_group *g) { return g ? (int)g->dev.size() : 0; }
+
+int mcts_group_device(const mcts_group *g, int i) { return (g && i >= 0 && i < (int)g->dev.size()) ? g->dev[i]->device : -1; }
+
+int mcts_group_get_timing(const mcts_group *g, mcts_timing *out)
+{
+    if (!g || !out) return fail(MCTS_EINVAL, "mcts_group_get_timing: NULL argument");
+    for (size_t i = 0; i < g->timing.size(); i++) out[i] = g->timing[i];
+    return MCTS_OK;
+}
+
+int mcts_group_simulate(mcts_group *g, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    if (!g || g->dev.empty() || !p || !agg) return fail(MCTS_EINVAL, "NULL argument");
+    const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
+    if (P <= 0) return fail(MCTS_EEMPTY, "zero paths (np.min of an empty list raises in the reference)");
+    const int n_dev = (int)g->dev.size();
+    mcts_options o;
+    memset(&o, 0, sizeof o);
+    if (opt) o = *opt;
+    o.chunk_paths = o.chunk_paths > 0 ? clamp_chunk(o.chunk_paths) : mcts_auto_chunk(P, n_dev);
+    const int64_t nc = mcts_plan_count(P, o.chunk_paths);
+    std::vector<int64_t> bounds((size_t)n_dev + 1);
+    int rc0 = mcts_plan_shards(P, o.chunk_paths, n_dev, bounds.data());
+    if (rc0) return rc0;
+    std::vector<mcts_chunk_result> recs((size_t)nc);
+    std::vector<int> rcs(n_dev, MCTS_OK);
+    std::vector<std::string> msgs(n_dev);
+    auto work = [&](int d) {
+        memset(&g->timing[d], 0, sizeof(mcts_timing));
+        if (bounds[d] >= bounds[d + 1]) return;
+        rcs[d] = simulate_range(g->dev[d], p, seed, &o, bounds[d], bounds[d + 1], recs.data() + bounds[d], profit, dd);
+        if (rcs[d]) msgs[d] = g_err;  // thread-local: hand the message to the calling thread
+        else g->timing[d] = g->dev[d]->timing;
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < n_dev; d++) {
+        try {
+            threads.emplace_back(work, d);
+        } catch (...) {  // no thread: evaluate that device's run from this thread after the others
+            rcs[d] = 1;
+        }
+    }
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int d = 1; d < n_dev; d++)
+        if (rcs[d] == 1) {
+            rcs[d] = MCTS_OK;
+            work(d);
+        }
+    for (int d = 0; d < n_dev; d++)
+        if (rcs[d]) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "device %d: ", g->dev[d]->device);
+            return fail(rcs[d], buf + msgs[d]);
+        }
+    return mcts_combine(P, o.chunk_paths, recs.data(), nc, agg);
 }
 
 }  // extern "C"

@@ -19,8 +19,17 @@ REC_BYTES = C.sizeof(_ffi.ChunkResult)
 
 
 def shard_bounds(n_chunks: int, world: int):
-    """Contiguous chunk ranges [lo, hi) per rank, balanced to within one chunk."""
+    """Contiguous chunk ranges [lo, hi) per rank, balanced to within one chunk (by chunk COUNT; the sharded
+    entry points below balance by path count through Engine.plan_shards)."""
     return [(n_chunks * r // world, n_chunks * (r + 1) // world) for r in range(world)]
+
+
+def resolve_chunk(P: int, chunk_paths: int, world: int) -> int:
+    """chunk_paths == 0 with several ranks: a chunk size that gives every rank at least four chunks.  The
+    single-device default (1 << 22) would leave any run of <= 4.19 M paths on ONE rank and an 8.39 M-path run on
+    four of eight.  Results are bit-identical for every chunk size; plan, evaluation and combine must merely agree
+    on it, which is why the resolved value is returned and used for all three."""
+    return int(chunk_paths) if chunk_paths and chunk_paths > 0 else (Engine.auto_chunk(P, world) if world > 1 else 0)
 
 
 def records_to_bytes(recs, n: int) -> np.ndarray:
@@ -59,9 +68,11 @@ def simulate_sharded(params, seed: int, compute_chunks, rank: int, world: int, c
     P = params.num_simulations * params.num_mc_shuffles
     if P <= 0:
         raise ValueError("zero paths")
+    if world > 1 and not (chunk_paths and chunk_paths > 0):
+        raise ValueError("simulate_sharded needs the resolved chunk size (resolve_chunk) so that compute_chunks uses the same plan")
     first, _ = Engine.plan(P, chunk_paths)
     n_chunks = len(first)
-    bounds = shard_bounds(n_chunks, world)
+    bounds = Engine.plan_shards(P, chunk_paths, world)
     lo, hi = bounds[rank]
     recs, n = compute_chunks(lo, hi)
     counts = [b - a for a, b in bounds]
@@ -77,6 +88,8 @@ def run_all_strategies_sharded(engine: Engine, params, seed: int, rank: int, wor
                                device=None, group=None):
     """The N-GPU form of run_all_strategies: every rank returns the same ranked 20-row table."""
     from .trading_models import summary_to_rows
+    P = params.num_simulations * params.num_mc_shuffles
+    chunk_paths = resolve_chunk(P, chunk_paths, world)
     opt = options if options is not None else engine.options(chunk_paths=chunk_paths)
     opt.chunk_paths = chunk_paths
 

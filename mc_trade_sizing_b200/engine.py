@@ -137,6 +137,18 @@ class Engine:
 
     # -- multi-device building blocks -----------------------------------------------------------
     @staticmethod
+    def auto_chunk(P: int, n_shards: int) -> int:
+        """Chunk size for a plan that is split over n_shards devices / ranks (mcts_auto_chunk)."""
+        return int(lib().mcts_auto_chunk(int(P), int(n_shards)))
+
+    @staticmethod
+    def plan_shards(P: int, chunk_paths: int, n_shards: int):
+        """Chunk ranges [lo, hi) per shard, contiguous and balanced by path count (mcts_plan_shards)."""
+        b = np.zeros(n_shards + 1, dtype=np.int64)
+        _raise(lib().mcts_plan_shards(int(P), int(chunk_paths), int(n_shards), b.ctypes.data_as(C.POINTER(C.c_int64))))
+        return [(int(b[r]), int(b[r + 1])) for r in range(n_shards)]
+
+    @staticmethod
     def plan(P: int, chunk_paths: int = 0):
         n = int(lib().mcts_plan_count(int(P), int(chunk_paths)))
         first, count = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
@@ -206,3 +218,56 @@ class Engine:
         d = C.c_double()
         _raise(lib().mcts_measure_step_ceiling(self._h, C.byref(d)))
         return {"fp64_inst_per_s": a.value, "int_inst_per_s": b.value, "sm_clock_mhz": c.value, "step_ceiling_per_s": d.value}
+
+
+class EngineGroup:
+    """Several B200s of one box behind one call (mcts_group_*): same simulate() contract and bit-identical results
+    as one Engine; the path range is cut into tree-node chunks, each device evaluates a contiguous run on its own
+    host thread inside libmcts, the chunk records are folded on the host in NumPy's order."""
+
+    def __init__(self, devices=None):
+        self._g = C.c_void_p()
+        if devices is None:
+            check(lib().mcts_group_create(None, 0, C.byref(self._g)))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib().mcts_group_create(arr, len(devices), C.byref(self._g)))
+        self.devices = [int(lib().mcts_group_device(self._g, i)) for i in range(int(lib().mcts_group_size(self._g)))]
+
+    def close(self):
+        if getattr(self, "_g", None) is not None and self._g.value:
+            lib().mcts_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    options = staticmethod(Engine.options)
+
+    def simulate(self, params: Params, seed: int = DEFAULT_SEED, per_path: bool = False, options: Options | None = None):
+        P = params.num_simulations * params.num_mc_shuffles
+        agg = (Agg * NSTRAT)()
+        profit = dd = None
+        if per_path and P > 0:
+            profit, dd = np.empty((NSTRAT, P)), np.empty((NSTRAT, P))
+        opt = options if options is not None else self.options()
+        _raise(lib().mcts_group_simulate(self._g, C.byref(params), C.c_uint64(seed & (2**64 - 1)), C.byref(opt), agg, _dp(profit), _dp(dd)))
+        out = {"agg": agg, "summary": agg_to_rows(agg, params.num_trades)}
+        if per_path:
+            out["profit"], out["dd"] = profit, dd
+        return out
+
+    def timing(self) -> list:
+        """Per-device timing of the last simulate()."""
+        t = (Timing * max(len(self.devices), 1))()
+        _raise(lib().mcts_group_get_timing(self._g, t))
+        return [{k: getattr(t[i], k) for k, _ in Timing._fields_} for i in range(len(self.devices))]

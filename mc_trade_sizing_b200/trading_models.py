@@ -10,18 +10,28 @@ Everything between the arguments and the 20-row result table runs on the B200 th
 (include/mcts.h).  There is no CPU fallback: without the library or a GPU the call raises.
 
 Extra knobs are environment variables so that the unchanged dps.py keeps working:
-    MCTS_SEED    Philox key (default 12345; the reference never seeds NumPy, so any seed is a valid run)
-    MCTS_DEVICE  CUDA device index (default 0)
-    MCTS_DEDUP   1 = evaluate the 11 distinct behaviours once and fan out (identical results)
-    MCTS_CHUNK   max paths per device chunk
+    MCTS_SEED     Philox key.  Unset: a fresh 64-bit key from os.urandom per call -- like the reference, which never
+                  seeds NumPy, two runs differ; the key used is kept in `last_seed` and, with MCTS_VERBOSE=1,
+                  written to stderr so that a run can be repeated
+    MCTS_DEVICE   CUDA device index (default 0)
+    MCTS_DEVICES  "all" or a comma-separated list: shard every call over several B200s inside libmcts
+                  (mcts_group_*; bit-identical results, no torchrun needed)
+    MCTS_DEDUP    1 = evaluate the 11 distinct behaviours once and fan out (identical results)
+    MCTS_CHUNK    max paths per device chunk
+    MCTS_SERVER   1 = hand the call to the per-user daemon (mc_trade_sizing_b200/server.py) that keeps the CUDA
+                  context and the engines alive between CLI invocations; started on first use
+
+This module imports nothing heavy at import time (no NumPy, no ctypes): the CLI's start-up cost is the
+interpreter's, which is what makes a daemon-served invocation take tens of milliseconds.
 """
 from __future__ import annotations
 
 import argparse
 import json as pyjson
 import os
+import sys
 
-from . import engine as _engine
+last_seed = None  # Philox key of the most recent run_all_strategies call in this process
 
 # strategy descriptions, reference src/trading_models.py:451-472 (they are the `Strategy` column of
 # every downstream sink: dps.py:362)
@@ -49,14 +59,51 @@ _DESCRIPTION_TEXT = (
 )
 DESCRIPTIONS = {i + 1: text for i, text in enumerate(_DESCRIPTION_TEXT)}
 
-_engines: dict[int, "_engine.Engine"] = {}
+_engines: dict = {}
 
 
-def get_engine(device: int | None = None) -> "_engine.Engine":
-    dev = int(os.environ.get("MCTS_DEVICE", "0")) if device is None else int(device)
-    if dev not in _engines:
-        _engines[dev] = _engine.Engine(dev)
-    return _engines[dev]
+def _device_spec(device):
+    """None -> MCTS_DEVICES / MCTS_DEVICE; returns an int (one device) or a tuple of ints / 'all' (a group)."""
+    if device is None:
+        many = os.environ.get("MCTS_DEVICES", "").strip()
+        if many:
+            device = many
+        else:
+            return int(os.environ.get("MCTS_DEVICE", "0"))
+    if isinstance(device, str):
+        if device.lower() == "all":
+            return "all"
+        ids = tuple(int(x) for x in device.split(",") if x.strip() != "")
+        return ids[0] if len(ids) == 1 else ids
+    if isinstance(device, (list, tuple)):
+        return int(device[0]) if len(device) == 1 else tuple(int(d) for d in device)
+    return int(device)
+
+
+def get_engine(device=None):
+    """The process-wide engine for a device (Engine) or a device list / 'all' (EngineGroup); created on first use."""
+    from . import engine as _engine
+    key = _device_spec(device)
+    if key not in _engines:
+        if key == "all":
+            _engines[key] = _engine.EngineGroup(None)
+        elif isinstance(key, tuple):
+            _engines[key] = _engine.EngineGroup(list(key))
+        else:
+            _engines[key] = _engine.Engine(key)
+    return _engines[key]
+
+
+def resolve_seed(seed=None) -> int:
+    """Explicit seed > MCTS_SEED > a fresh key from os.urandom (the reference is unseeded: reruns must differ)."""
+    global last_seed
+    if seed is None:
+        env = os.environ.get("MCTS_SEED")
+        seed = int(env) if env not in (None, "") else int.from_bytes(os.urandom(8), "little")
+    last_seed = int(seed) & (2 ** 64 - 1)
+    if os.environ.get("MCTS_VERBOSE") == "1":
+        print("[mcts] seed=%d" % last_seed, file=sys.stderr)
+    return last_seed
 
 
 def rank_rows(rows):
@@ -70,7 +117,7 @@ def rank_rows(rows):
 
 
 def summary_to_rows(summary):
-    """[20,9] array in strategy-id order -> the reference's list of 10-tuples (:522), ranked."""
+    """[20,9] values in strategy-id order -> the reference's list of 10-tuples (:522), ranked."""
     import numpy as np
     rows = [(DESCRIPTIONS[i + 1],) + tuple(np.float64(x) for x in summary[i]) for i in range(20)]
     return rank_rows(rows)
@@ -85,9 +132,18 @@ def run_all_strategies(
     """Same signature and return value as the reference (src/trading_models.py:445-450, :522-530):
     a ranked list of 20 tuples (description, avg_profit, avg_drawdown, ratio, min_profit, max_profit,
     min_dd, max_dd, avg_per_trade, ratio_max_dd).  The keyword-only extras default from MCTS_* env."""
-    seed = int(os.environ.get("MCTS_SEED", str(_engine.DEFAULT_SEED))) if seed is None else int(seed)
+    seed = resolve_seed(seed)
     dedup = os.environ.get("MCTS_DEDUP", "0") == "1" if dedup is None else bool(dedup)
     chunk_paths = int(os.environ.get("MCTS_CHUNK", "0")) if chunk_paths is None else int(chunk_paths)
+    if os.environ.get("MCTS_SERVER") == "1":
+        from . import server
+        return rank_rows(server.client_run(
+            [hit_rate, avg_win, avg_loss, num_trades, num_simulations, num_mc_shuffles],
+            dict(use_markov=bool(use_markov), p_win_after_win=p_win_after_win, p_win_after_loss=p_win_after_loss,
+                 use_markov2=bool(use_markov2), p_win_ww=p_win_ww, p_win_wl=p_win_wl, p_win_lw=p_win_lw, p_win_ll=p_win_ll,
+                 use_regime=bool(use_regime), regimes=regimes),
+            seed=seed, device=_device_spec(device), dedup=dedup, chunk_paths=chunk_paths))
+    from . import engine as _engine
     params = _engine.make_params(
         hit_rate, avg_win, avg_loss, num_trades, num_simulations, num_mc_shuffles,
         use_markov=use_markov, p_win_after_win=p_win_after_win, p_win_after_loss=p_win_after_loss,
@@ -168,24 +224,28 @@ def format_row(row):
 
 
 def settings_block(args):
-    """The header the scraper reads (dps.py:145-154): reference :552-584."""
+    """The header the scraper reads (dps.py:145-154): reference :552-584.  A generator: main() prints every line as
+    it is produced, so the output up to a failure is the reference's too (for avg_win <= 0 the reference prints the
+    settings, then find_break_even_hit_rate's error line, then dies formatting None -- :583-584)."""
     key = _mode_key(args)
     bar = "=" * 90
-    out = ["\n" + bar, "CURRENT SIMULATION SETTING:", f"Hit rate: {args.hit_rate:.2%}", "Mode: " + MODE_NAMES[key]]
+    yield "\n" + bar
+    yield "CURRENT SIMULATION SETTING:"
+    yield f"Hit rate: {args.hit_rate:.2%}"
+    yield "Mode: " + MODE_NAMES[key]
     if key == "regime" and args.regimes:
-        out.append(f"Regimes: {args.regimes}")
+        yield f"Regimes: {args.regimes}"
     elif key == "markov2":
-        out.append(f"P(win|WW): {args.p_win_ww}, P(win|WL): {args.p_win_wl}, P(win|LW): {args.p_win_lw}, P(win|LL): {args.p_win_ll}")
+        yield f"P(win|WW): {args.p_win_ww}, P(win|WL): {args.p_win_wl}, P(win|LW): {args.p_win_lw}, P(win|LL): {args.p_win_ll}"
     elif key == "markov1":
-        out.append(f"P(win|win): {args.p_win_after_win}, P(win|loss): {args.p_win_after_loss}")
-    out.append(bar + "\n")
+        yield f"P(win|win): {args.p_win_after_win}, P(win|loss): {args.p_win_after_loss}"
+    yield bar + "\n"
     for label, value in (("Average win per trade: €", args.avg_win), ("Average loss per trade: €", args.avg_loss),
                          ("Number of simulations: ", args.num_simulations), ("Number of trades per simulation: ", args.num_trades),
                          ("Number of shuffles per simulation: ", args.num_mc_shuffles)):
-        out.append(f"{label}{value}")
-    breakeven = find_break_even_hit_rate(args.avg_win, args.avg_loss, MODE_NAMES[key])
-    out.append(f"Break-even hit rate: {breakeven:.2%}")
-    return out
+        yield f"{label}{value}"
+    breakeven = find_break_even_hit_rate(args.avg_win, args.avg_loss, MODE_NAMES[key])  # prints its own error line
+    yield f"Break-even hit rate: {breakeven:.2%}"  # TypeError for None, exactly like :584
 
 
 def main(argv=None):

@@ -85,3 +85,23 @@ def test_shard_bounds_cover_all_chunks():
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_auto_chunk_gives_every_rank_work():
+    """with the single-device default chunk (1 << 22) a run of <= 4.19 M paths is ONE chunk and an
+    8.39 M-path run is four, so most of eight ranks idled.  resolve_chunk + plan_shards must hand every rank a
+    contiguous, non-empty, balanced run whenever there are enough paths, and cover the plan exactly."""
+    from mc_trade_sizing_b200 import Engine
+    from mc_trade_sizing_b200.distributed import resolve_chunk
+    for P in (40_000, 1_000_000, 4_194_304, 8_388_640, 67_109_120, 10 ** 9):
+        for world in (2, 3, 4, 8):
+            ch = resolve_chunk(P, 0, world)
+            first, count = Engine.plan(P, ch)
+            b = Engine.plan_shards(P, ch, world)
+            assert b[0][0] == 0 and b[-1][1] == len(first) and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            per = [int(count[lo:hi].sum()) for lo, hi in b]
+            assert sum(per) == P
+            if P >= 16384 * 4 * world:
+                assert min(per) > 0, (P, world, per)
+                assert max(per) * world <= 1.3 * P, (P, world, per)
+    assert resolve_chunk(10 ** 6, 0, 1) == 0 and resolve_chunk(10 ** 6, 4096, 8) == 4096

@@ -53,8 +53,9 @@ for name, args, kw, expect in CONFIGS:
     if world == 1:
         rows = eng.simulate(prm, seed=2026)["summary"]
     else:
-        _, rows = mdist.simulate_sharded(prm, 2026, lambda lo, hi: eng.simulate_chunks(prm, 2026, lo, hi, options=eng.options()), rank, world,
-                                         chunk_paths=0, device=device)
+        ch = mdist.resolve_chunk(P, 0, world)   # every rank gets chunks, also for the 1,000-path configs' single chunk
+        _, rows = mdist.simulate_sharded(prm, 2026, lambda lo, hi: eng.simulate_chunks(prm, 2026, lo, hi, options=eng.options(chunk_paths=ch)), rank, world,
+                                         chunk_paths=ch, device=device)
     wall = time.perf_counter() - t0
     if rank == 0:
         print("%-52s wall %9.3f ms  %.3e trade-steps/s  avg_profit[1] = %.3f (analytic %.1f)  avg_dd[1] = %.3f"

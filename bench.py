@@ -32,7 +32,11 @@ CHUNK_PATHS = 1 << 22          # the library default: two 4.19 M-path chunks per
 METRIC = "trade-steps/sec (paths x trades x strategies)"
 UNIT = "trade-steps/s"
 FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)
-TRAFFIC_PER_LAUNCH = 642.2e6         # dram bytes read + written by one k_sim_paths launch (ncu --set full, profiles/)
+TRAFFIC_PER_LAUNCH = 642.2e6         # dram bytes read + written by one k_sim_paths launch: a CONSTANT from the committed
+TRAFFIC_SOURCE = "ncu constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r02_ncu_bench_sim_paths.txt (not re-measured by bench.py)"
+C5_FULL_SIMS = 50_000_000            # x 20 shuffles = 1e9 paths: BASELINE.json config 5 at its stated size
+STRONG_SIMS = 3_355_456              # x 20 = 67,109,120 paths: the FIXED problem of the strong-scaling line (8 x the per-GPU batch)
+SHA_SIMS, SHA_SHUFFLES = 1 << 20, 16  # 2^24 paths: the fixed run whose summary hash must not depend on the number of GPUs
 
 
 def workload_config(n_gpus):
@@ -122,6 +126,48 @@ def cpu_reference_rate(target_seconds=12.0, cores=None):
             "seconds": secs, "trade_steps": steps}
 
 
+def python_reference_rates(cores=None):
+    """The REAL Python reference (an unmodified copy under baseline/_ref, see baseline/install_ref.py) timed on this
+    box's host cores the way BASELINE.md section 3 prescribes: in-process run_all_strategies, NumPy seeded per worker,
+    (1) one core per generator mode at 10 x 20 = 200 paths, (2) one worker per host core, (3) three concurrent workers
+    (what dps.py:268 achieves).  Each worker is a separate process (baseline/ref_worker.py); a group's aggregate rate is
+    its total trade-steps over the slowest worker's time inside the call."""
+    worker = os.path.join(ROOT, "baseline", "ref_worker.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "src", "trading_models.py")):
+        return {"unavailable": "baseline/_ref is not populated (python baseline/install_ref.py needs /root/reference, which exists only in the build container)"}
+    cores = cores or host_cores()
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+
+    def group(jobs):
+        start_at = time.time() + 2.0 + 0.02 * len(jobs)        # every worker finishes its imports first
+        procs = [subprocess.Popen([sys.executable, worker, mode, str(sims), str(sh), str(seed), repr(start_at)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True, env=env) for mode, sims, sh, seed in jobs]
+        outs = []
+        for pr in procs:
+            out, _ = pr.communicate(timeout=600)
+            if pr.returncode == 0 and out.strip():
+                outs.append(json.loads(out.strip().splitlines()[-1]))
+        return outs
+
+    try:
+        t0 = time.time()
+        one = group([(m, 10, 20, 12345) for m in ("shuffle", "markov1", "markov2", "regime")])
+        allc = group([("shuffle", 5, 20, 100 + i) for i in range(cores)])
+        three = group([("shuffle", 5, 20, 200 + i) for i in range(3)])
+        agg = lambda outs: sum(o["trade_steps"] for o in outs) / max(o["seconds"] for o in outs) if outs else None
+        return {
+            "kind": "reference", "unit": UNIT, "impl": "unmodified src/trading_models.py run_all_strategies, in process, np.random.seed per worker",
+            "one_core": {o["mode"]: o["trade_steps"] / o["seconds"] for o in one},
+            "one_core_sample": "10 sims x 20 shuffles x 1000 trades x 20 strategies per mode (parameters of configs C1-C4), one process per mode",
+            "all_cores": {"value": agg(allc), "cores": len(allc), "sample": "%d workers x 5 sims x 20 shuffles x 1000 trades x 20 strategies (C5 parameters)" % len(allc)},
+            "three_procs": {"value": agg(three), "cores": len(three), "sample": "3 workers x 5 x 20 paths: the concurrency dps.py:268 uses"},
+            "avg_profit_strategy1": one[0]["avg_profit_strategy1"] if one else None,
+            "seconds": time.time() - t0,
+        }
+    except Exception as e:  # a baseline must never cost the bench line
+        return {"unavailable": "python reference run failed: %r" % (e,)}
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU path on the box's host cores (all threads), same
     metric / config.  Rank 0 alone runs it."""
@@ -141,13 +187,22 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": per_step[-1]["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": per_step[-1]["sample"],
+                         "python_reference": python_reference_rates(cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python (no compilable sources): this arm times oracle/mcts_oracle.c, the C restatement "
-                "pinned bit-exact to it, on all host threads; each step is a bounded sample of the C5 workload",
+        "note": "the reference is pure Python (no compilable sources): the VALUE of this arm is oracle/mcts_oracle.c, the C restatement "
+                "pinned bit-exact to it, on all host threads -- about 100x faster per core than the Python original, i.e. the "
+                "conservative denominator; the Python original itself is timed beside it under cpu_baseline.python_reference. "
+                "Each step is a bounded sample of the C5 workload (config.sample_paths_per_step), not the full batch",
     }
+    line["config"]["sample_paths_per_step"] = int(per_step[-1]["trade_steps"] // (NUM_TRADES * 20))
     print(json.dumps(line), flush=True)
+
+
+def np_bytes(rows):
+    import numpy as np
+    return np.ascontiguousarray(np.asarray(rows, dtype=np.float64)).tobytes()
 
 
 def main():
@@ -182,8 +237,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device; libmcts has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        host_group = dist.new_group(backend="gloo")   # CPU-side waits: ranks that idle must not spin on their GPU
     n_gpus = world
 
     eng = Engine(local_rank)
@@ -263,8 +320,7 @@ def main():
     # that the CUDA events around each k_sim_paths launch do not overlap a neighbouring launch
     kstat = {"paths_ms": 0.0, "paths_launches": 0, "trade_steps": 0, "total_ms": 0.0}
     opt_serial = eng.options(chunk_paths=CHUNK_PATHS, serial_chunks=True)
-    n_chunks = len(Engine.plan(P, CHUNK_PATHS)[0])
-    lo, hi = mdist.shard_bounds(n_chunks, world)[rank]
+    lo, hi = Engine.plan_shards(P, CHUNK_PATHS, world)[rank]
     for s in range(3):
         eng.simulate_chunks(prm, 7000 + s, lo, hi, options=opt_serial)
         if s == 0:
@@ -299,6 +355,15 @@ def main():
             t64 = eng.timing()
             extras["other_configs"][name] = {"value": t["trade_steps"] / (t["total_ms"] * 1e-3),
                                              "value_fp64_evaluator": t64["trade_steps"] / (t64["total_ms"] * 1e-3), "unit": UNIT}
+        # (a2b) worst case for generation: ONE shuffle per simulation, so the base sequence (1000 53-bit uniforms) is not amortised
+        extras["gen_worst_case"] = {}
+        for name, kw in (("dynamic_fp64", {}), ("markov2_int32", kws["markov2_c3"])):
+            pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, 2097140, 1, **kw)
+            for sd in (1, 2):
+                eng.simulate(pm, seed=sd, options=eng.options(chunk_paths=CHUNK_PATHS, serial_chunks=True))
+            t = eng.timing()
+            extras["gen_worst_case"][name] = {"value": t["trade_steps"] / (t["total_ms"] * 1e-3), "unit": UNIT, "num_mc_shuffles": 1,
+                                              "gen_base_share_of_step": t["gen_ms"] / max(t["total_ms"], 1e-9)}
         # (a3) replay mode end to end: caller sequences in (pageable) host memory -> C ABI -> per-strategy aggregates
         import numpy as np
         n_rep = 200000
@@ -324,11 +389,81 @@ def main():
         extras["curve_export"] = {"trade_steps_per_s": t["trade_steps"] / (t["paths_ms"] * 1e-3), "achieved_gbs": gbs,
                                   "bytes_per_trade_step": 8, "paths": n_curve}
 
+    # ---- lines every rank takes part in: the fixed-size problems (BASELINE.json config 5 is a STRONG-scaling statement) ----
+    import hashlib
+
+    def sharded_rows(pm, seed, chunk=0):
+        """run_all_strategies on all N GPUs of this job through the public entry points (every rank gets the table)."""
+        if world == 1:
+            return eng.simulate(pm, seed=seed, options=eng.options(chunk_paths=chunk))["summary"], eng.timing()["total_ms"]
+        ch = mdist.resolve_chunk(pm.num_simulations * pm.num_mc_shuffles, chunk, world)
+        _, rows = mdist.simulate_sharded(pm, seed, lambda lo_, hi_: eng.simulate_chunks(pm, seed, lo_, hi_, options=eng.options(chunk_paths=ch)),
+                                         rank, world, chunk_paths=ch, device=device)
+        return rows, eng.timing()["total_ms"]
+
+    def timed_job(pm, seed, reps):
+        best = None
+        for r in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            rows, dev_ms_local = sharded_rows(pm, seed + r)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            tt = torch.tensor([wall, dev_ms_local * 1e-3], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if best is None or float(tt[0]) < best[0]:
+                best = (float(tt[0]), float(tt[1]), rows)
+        return best
+
+    if not args.no_extras:
+        # (c) strong scaling: ONE fixed problem (67,109,120 paths) split over however many GPUs there are
+        pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, STRONG_SIMS, NUM_SHUFFLES)
+        wall, dev_s, rows = timed_job(pm, 31000, 3)
+        tsteps = STRONG_SIMS * NUM_SHUFFLES * NUM_TRADES * 20
+        extras["strong_scaling"] = {"paths_total": STRONG_SIMS * NUM_SHUFFLES, "n_gpus": n_gpus, "ms_per_step": wall * 1e3, "device_ms_per_step_max_over_ranks": dev_s * 1e3,
+                                    "value": tsteps / wall, "unit": UNIT, "scaling": "strong",
+                                    "note": "fixed problem; wall time of the whole sharded call (best of 3), max over ranks"}
+        # (d) BASELINE.json config 5 at its stated size: 1e9 paths x 1000 trades x 20 strategies
+        pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, C5_FULL_SIMS, NUM_SHUFFLES)
+        wall, dev_s, rows = timed_job(pm, 2026, 1)
+        extras["c5_full"] = {"paths": C5_FULL_SIMS * NUM_SHUFFLES, "trade_steps": C5_FULL_SIMS * NUM_SHUFFLES * NUM_TRADES * 20, "n_gpus": n_gpus, "wall_s": wall,
+                             "value": C5_FULL_SIMS * NUM_SHUFFLES * NUM_TRADES * 20 / wall, "unit": UNIT, "seed": 2026,
+                             "avg_profit_strategy1": float(rows[0][0]), "avg_drawdown_strategy1": float(rows[0][1]), "analytic_avg_profit_strategy1": 103063.2,
+                             "summary_sha256": hashlib.sha256(np_bytes(rows)).hexdigest()}
+    # (e) partition invariance, driver-visible: the summary of one fixed 2^24-path run must hash the same for every N
+    pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, SHA_SIMS, SHA_SHUFFLES)
+    rows, _ = sharded_rows(pm, 4711)
+    partition_sha = hashlib.sha256(np_bytes(rows)).hexdigest()
+
     if rank != 0:
         if world > 1:
-            dist.barrier()   # rank 0 may still be running its side measurements
+            dist.barrier(group=host_group)   # rank 0 may still be running its single-process measurements (CPU-side wait)
+            dist.barrier()
             dist.destroy_process_group()
         return
+
+    # (f) the same fixed run through the UNCHANGED API from ONE process driving all N GPUs inside libmcts (no torchrun
+    #     needed by a user; the other ranks of this job idle on a CPU-side barrier meanwhile)
+    inlib = None
+    try:
+        from mc_trade_sizing_b200 import EngineGroup
+        with EngineGroup(list(range(n_gpus))) as grp:
+            grp.simulate(pm, seed=1)
+            t0 = time.perf_counter()
+            out = grp.simulate(pm, seed=4711)
+            wall = time.perf_counter() - t0
+            inlib = {"devices": grp.devices, "summary_sha256": hashlib.sha256(np_bytes(out["summary"])).hexdigest(), "wall_ms": wall * 1e3,
+                     "value": SHA_SIMS * SHA_SHUFFLES * NUM_TRADES * 20 / wall, "unit": UNIT,
+                     "api": "mcts_group_simulate behind run_all_strategies (MCTS_DEVICES): one process, one host thread per device"}
+            if not args.no_extras and n_gpus > 1:
+                pm_s = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, STRONG_SIMS, NUM_SHUFFLES)
+                grp.simulate(pm_s, seed=2)
+                t0 = time.perf_counter()
+                grp.simulate(pm_s, seed=3)
+                inlib["strong_scaling_ms"] = (time.perf_counter() - t0) * 1e3
+    except Exception as e:
+        inlib = {"error": repr(e)}
 
     peaks_file = {}
     try:
@@ -350,7 +485,9 @@ def main():
         "frac": achieved_tflops / peak_tflops,
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_sim_paths launch of this workload (2,097,160 paths), from the
         # committed `ncu --set full` capture profiles/r01_ncu_bench_sim_paths.txt; algorithmic bytes per launch = paths x 320 B
-        "traffic": TRAFFIC_PER_LAUNCH, "traffic_unit": "B per launch", "algorithmic_bytes_per_launch": 2097160 * 320,
+        "traffic": TRAFFIC_PER_LAUNCH, "traffic_unit": "B per launch", "traffic_source": TRAFFIC_SOURCE, "algorithmic_bytes_per_launch": 2097160 * 320,
+        "peak_source": "in-process microbenchmark k_peak_dadd (mcts_measure_peaks): independent DADD chains over the whole chip, measured by "
+                       "this run; MEASURED_PEAKS.json has no fp64 figure",
         "bound_note": "neither HBM (0.016 B per trade-step) nor tensor cores (no contraction) bound this kernel; SURVEY 8(d) "
                       "prescribes the SM issue / FP64-pipe roofline used here; the HBM roofline of curve-export mode is under curve_export",
         "definition": "achieved = 6 algorithmic fp64 ops per trade-step (SURVEY 8d) x trade-steps per launch / mean launch "
@@ -384,14 +521,20 @@ def main():
         "gpu_launches": int(stat["launches"]),
         "clocks": clocks, "roofline": roofline,
         "result_check": {"avg_profit_strategy1": float(last[1][0][0]), "expected": 103063.2},
+        "partition_sha": partition_sha,
+        "partition_sha_of": "sha256 of the [20,9] summary of the fixed run %d sims x %d shuffles x 1000 trades, seed 4711, sharded over this job's %d GPU(s): "
+                            "must be identical for every N" % (SHA_SIMS, SHA_SHUFFLES, n_gpus),
+        "inlib_multi_gpu": inlib,
     }
     line.update(extras)
     if not args.no_cpu_baseline and n_gpus == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["python_reference"] = python_reference_rates()
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier(group=host_group)
         dist.barrier()
         dist.destroy_process_group()
 

@@ -47,8 +47,13 @@ typedef enum {
     MCTS_ECUDA = -4,      /* CUDA runtime error, message has the details */
     MCTS_ENODEVICE = -5,  /* no usable CUDA device / wrong architecture: there is no CPU fallback */
     MCTS_EUNSUPPORTED = -6 /* valid for the reference but outside this build's limits (see message):
-                              > ~260,000 trades per path, > 16 regimes, non-finite or subnormal trade values
-                              in simulate mode, curve export of runs with > 16 distinct values */
+                              > ~260,000 trades per path, > 16 regimes, subnormal trade values in simulate
+                              mode, curve export of runs with > 16 distinct values, and NON-FINITE ARITHMETIC:
+                              NaN / infinite trade values, or equity / profit sums beyond DBL_MAX (simulate:
+                              3 * max|value| * trades >= DBL_MAX is refused up front; replay: detected on the
+                              device).  The reference reports NaN drawdowns in those cases (np.min propagates
+                              NaN); the kernels' ordered comparisons would drop the NaN, so the call fails
+                              instead of returning numbers that differ from the reference's. */
 } mcts_status;
 
 /* Generator selection, same precedence as trading_models.py:477-490. */
@@ -147,7 +152,8 @@ int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mct
 /*
  * Replay: evaluate caller-supplied post-shuffle sequences (replaces :493-507 + :509-518).
  *   values    [P][T] row-major trade results (what np.random.shuffle left in base_results); any finite
- *             doubles, including zeros of either sign and the reference's int64 regime arrays
+ *             doubles, including zeros of either sign and the reference's int64 regime arrays; a NaN or
+ *             infinite value, or sums beyond DBL_MAX, fail the call with MCTS_EUNSUPPORTED (see there)
  *   profit,dd optional [20][P]
  */
 int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt,
@@ -193,7 +199,7 @@ int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *boun
 typedef struct mcts_group mcts_group;
 
 /* devices == NULL or n <= 0: every visible compute-capability-10.x device.  Fails with MCTS_ENODEVICE
- * if there is none. */
+ * if there is none.  A device may be listed more than once (every entry gets its own handle). */
 int mcts_group_create(const int *devices, int n, mcts_group **out);
 void mcts_group_destroy(mcts_group *g);
 int mcts_group_size(const mcts_group *g);

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcts.so")
 SOURCES = ["mcts.cu", "paths_full.cu", "paths_dedup.cu", "paths_int.cu", "paths_curves.cu"]
-HEADERS = ["stager.hpp", "kernels.cuh", "paths_launch.cuh", "eval_core.cuh", "gen_core.cuh", "pairwise.cuh", "planner.hpp", "spec.hpp",
+HEADERS = ["stager.hpp", "kernels.cuh", "aux_kernels.cuh", "paths_launch.cuh", "eval_core.cuh", "gen_core.cuh", "pairwise.cuh", "planner.hpp", "spec.hpp",
            os.path.join("..", "..", "include", "mcts.h")]
 
 NVCC_FLAGS = [

@@ -69,10 +69,10 @@ struct IdList {
 // body: the lists below are the best of a search (tools/pass_search) scored by the SASS instruction count of
 // the loop bodies and confirmed on the B200.
 #ifndef MCTS_FP0
-#define MCTS_FP0 4, 5, 14, 17, 8
-#define MCTS_FP1 9, 10, 15, 11, 12
-#define MCTS_FP2 1, 3, 2, 13, 16
-#define MCTS_FP3 6, 7, 18, 19, 20
+#define MCTS_FP0 3, 18, 11, 1, 12
+#define MCTS_FP1 14, 4, 5, 8, 17
+#define MCTS_FP2 6, 7, 19, 16, 20
+#define MCTS_FP3 13, 9, 15, 2, 10
 #endif
 using FullPass0 = IdList<MCTS_FP0>;
 using FullPass1 = IdList<MCTS_FP1>;
@@ -398,8 +398,11 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
 //        uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
 //        get<i>() / get_dyn(i)
 //   OPAQUE: every id's chains start from constant memory (ids of one class in one pass stay separate chains)
+//   returns true when an equity or a profit sum left the finite range (non-finite input values, or sums beyond
+//   DBL_MAX): the reference's drawdown is NaN then (np.min propagates it) while the ordered comparisons used here
+//   drop NaNs, so such paths are outside the bit-exactness contract and the replay entry point rejects them.
 template <class IDS, int SEL = 0, bool OPAQUE = false, class SRC, class SINK>
-MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, double (&profit)[IDS::N], double (&drawdown)[IDS::N])
+MCTS_HD bool eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, double (&profit)[IDS::N], double (&drawdown)[IDS::N])
 {
     constexpr int NS = IDS::N;
     Acc<NS> a;
@@ -443,11 +446,15 @@ MCTS_HD void eval_path(SRC &src, SINK &sink, const LeafSched *__restrict__ sch, 
             for (int s = 0; s < NS; s++) stk[s][sp - 1] = stk[s][sp - 1] + stk[s][sp];
         }
     }
+    bool nonfinite = false;
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         profit[s] = 0.0 + stk[s][0];  // np.add.reduce starts from the identity 0.0
         drawdown[s] = a.dd[s];
+        // x - x is 0 for finite x and NaN for +-inf / NaN; a non-finite equity never becomes finite again
+        nonfinite = nonfinite || (a.E[s] - a.E[s] != 0.0) || (profit[s] - profit[s] != 0.0);
     }
+    return nonfinite;
 }
 
 // ---- exact int32 evaluator -----------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/mcts.h"
+#include "aux_kernels.cuh"
 #include "kernels.cuh"
 #include "planner.hpp"
 #include "stager.hpp"
@@ -65,6 +66,7 @@ struct mcts_handle {
     int64_t cap_recs = 0;
     LeafSched *d_sched = nullptr;
     int64_t sched_L = -1;
+    uint32_t *d_flags = nullptr;  // replay: non-finite equity / profit seen (kernels.cuh PathArgs::flags)
     // replay: two staging areas for caller sequences (chunk c+1 is copied while chunk c is evaluated)
     double *d_values[2] = {nullptr, nullptr};
     int64_t cap_values[2] = {0, 0};
@@ -170,6 +172,7 @@ static int init_handle(mcts_handle *h)
     CUDA_TRY(cudaEventCreate(&h->ev_begin));
     CUDA_TRY(cudaEventCreate(&h->ev_end));
     CUDA_TRY(cudaMalloc(&h->d_sched, sizeof(LeafSched)));
+    CUDA_TRY(cudaMalloc(&h->d_flags, sizeof(uint32_t)));
     memset(&h->timing, 0, sizeof h->timing);
     return MCTS_OK;
 }
@@ -226,6 +229,7 @@ void mcts_destroy(mcts_handle *h)
     }
     cudaFree(h->d_recs);
     cudaFree(h->d_sched);
+    cudaFree(h->d_flags);
     for (int i = 0; i < 2; i++) {
         cudaFree(h->d_values[i]);
         if (h->values_free[i]) cudaEventDestroy(h->values_free[i]);
@@ -667,6 +671,7 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
     }
     if (!h->stager.ready()) CUDA_TRY(h->stager.init(h->device));
     if ((rc = ensure(&h->d_recs, &h->cap_recs, nc))) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
     for (int64_t c = 0; c < nc; c++) {
         const int64_t f = first[c], n = count[c];
@@ -682,6 +687,7 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
         a.sched = h->d_sched;
         a.out = L.d_out;
         a.ld = L.cap_paths;
+        a.flags = h->d_flags;
         if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
         launch_replay_passes(h, h->stream, mode, a, d_vals, T);
         CUDA_TRY(cudaGetLastError());
@@ -694,9 +700,14 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
     std::vector<mcts_chunk_result> recs((size_t)nc);
     CUDA_TRY(cudaMemcpyAsync(recs.data(), h->d_recs, sizeof(mcts_chunk_result) * (size_t)nc, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t flags = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flags, h->d_flags, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * nc;
+    h->timing.d2h_bytes += (int64_t)sizeof(mcts_chunk_result) * nc + (int64_t)sizeof flags;
     if ((rc = timing_collect(h))) return rc;
+    if (flags & 1u)
+        return fail(MCTS_EUNSUPPORTED, "replay: a trade value is NaN or infinite, or an equity / profit sum exceeded DBL_MAX; the reference yields "
+                                       "NaN drawdowns there (np.min propagates NaN), which this build does not reproduce");
     return mcts_combine(P, chunk, recs.data(), nc, agg);
 }
 
@@ -944,10 +955,7 @@ int mcts_group_create(const int *devices, int n, mcts_group **out)
         }
         if (ids.empty()) return fail(MCTS_ENODEVICE, "no compute-capability-10.x device visible; libmcts is built for sm_100a only");
     } else {
-        ids.assign(devices, devices + n);
-        for (size_t i = 0; i < ids.size(); i++)
-            for (size_t j = 0; j < i; j++)
-                if (ids[i] == ids[j]) return fail(MCTS_EINVAL, "mcts_group_create: a device is listed twice");
+        ids.assign(devices, devices + n);  // a device may appear more than once: every entry gets its own handle and streams
     }
     mcts_group *g = new (std::nothrow) mcts_group();
     if (!g) return fail(MCTS_ENOMEM, "out of host memory");

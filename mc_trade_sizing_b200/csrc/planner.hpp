@@ -176,6 +176,12 @@ inline int build_spec(const mcts_params &p, GenSpec *out, std::string *err)
             if (fabs(v) > vmax) vmax = fabs(v);
         }
         if (g.all_int && 6.0 * vmax * (double)g.L >= 2147483648.0) g.all_int = 0;
+        // equity and profit sums are bounded by 3 * max|v| * L: keep them finite, so that no NaN can arise (inf - inf in
+        // the drawdown; the reference would report NaN there, the ordered comparisons of the kernels would drop it)
+        if (vmax > 1.7976931348623157e308 / (3.0 * (double)g.L)) {
+            *err = "trade values too large: 3 * max|value| * trades must stay below DBL_MAX in simulate mode";
+            return MCTS_EUNSUPPORTED;
+        }
     }
     *out = g;
     return MCTS_OK;

@@ -36,6 +36,17 @@ def stats_golden():
 
 
 @pytest.fixture(scope="session")
+def full_golden():
+    """BASELINE configs C1 / C2 at their stated size (1,000 paths x 1,000 trades) captured from the live reference;
+    the sequences are stored as a value table + uint8 codes and expanded here."""
+    d = _load("full.npz")
+    d["meta"] = json.loads(str(d["meta"]))
+    for name in d["meta"]:
+        d[name + "/seqs"] = np.ascontiguousarray(d[name + "/values"][d[name + "/codes"]])
+    return d
+
+
+@pytest.fixture(scope="session")
 def rng_golden():
     return _load("rng.npz")
 

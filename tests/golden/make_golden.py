@@ -12,7 +12,12 @@ NumPy RandomState is seeded by this harness (the reference never seeds), and
 the post-shuffle sequence and the per-path (profit, drawdown) of every strategy
 without touching reference source.
 
+    python tests/golden/make_golden.py --full     # full.npz only (~1 min)
+
 Outputs (committed):
+    full.npz    BASELINE configs C1 and C2 at their stated size (50 simulations x 20 shuffles = 1,000 paths x
+                1,000 trades) from the live reference: sequences (as a value table + uint8 codes), per-path
+                results of all 20 strategies, ranked summary rows
     kat.npz     seeded known-answer runs: sequences, per-path results, summaries
     stats.npz   larger per-path samples per mode for statistical tests of the
                 device RNG path
@@ -159,8 +164,34 @@ def main():
     print("numpy", np.__version__, "python", sys.version.split()[0])
 
 
-if __name__ == "__main__" and "--cli" not in sys.argv:
+def make_full_golden():
+    """C1 and C2 of BASELINE.json at full size, from the live reference."""
+    tm = load_reference()
+    desc = descriptions_by_id(tm)
+    desc_to_id = {v: k for k, v in desc.items()}
+    out, meta = {}, {}
+    for name, seed, args, kw in (("c1_full", 20261, (0.82, 186.0, 219.0, 1000, 50, 20), MODE_KW["dynamic"]),
+                                 ("c2_full", 20262, (0.82, 186.0, 219.0, 1000, 50, 20), MODE_KW["markov1"])):
+        r = capture_run(tm, seed, args, kw)
+        table, codes = np.unique(r["seqs"], return_inverse=True)   # <= 6 distinct trade values per run
+        assert table.size <= 255 and (table[codes.reshape(r["seqs"].shape)].view(np.uint64) == r["seqs"].view(np.uint64)).all()
+        out[name + "/values"] = table
+        out[name + "/codes"] = codes.reshape(r["seqs"].shape).astype(np.uint8)
+        out[name + "/profit"] = r["profit"]
+        out[name + "/dd"] = r["dd"]
+        out[name + "/rank_ids"] = np.array([desc_to_id[row[0]] for row in r["rows"]], dtype=np.int32)
+        out[name + "/rows"] = np.array([[float(x) for x in row[1:]] for row in r["rows"]], dtype=np.float64)
+        meta[name] = {"seed": seed, "args": list(args), "kwargs": kw}
+        print("full", name, r["seqs"].shape, table)
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "full.npz"), **out)
+
+
+if __name__ == "__main__" and "--full" in sys.argv:
+    make_full_golden()
+elif __name__ == "__main__" and "--cli" not in sys.argv:
     main()
+    make_full_golden()
 
 
 def make_cli_golden():

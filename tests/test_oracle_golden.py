@@ -48,6 +48,23 @@ def test_replay_entry_matches_reference_per_path(kat):
         assert_bitexact(out["summary"][ids - 1], kat[name + "/rows"], name + " summary rows")
 
 
+def test_full_size_c1_c2_reproduce_reference(full_golden):
+    """BASELINE configs C1 (No Markov) and C2 (Markov-1) at their stated 1,000 paths x 1,000 trades: seeded oracle
+    run == live reference (sequences, all 20 x 1,000 per-path results, ranked rows), and the replay entry agrees."""
+    for name in sorted(full_golden["meta"]):
+        meta = full_golden["meta"][name]
+        out = oracle.run_all(_params(meta), meta["seed"], per_path=True, sequences=True)
+        assert out["seqs"].shape == (1000, 1000)
+        assert_bitexact(out["seqs"], full_golden[name + "/seqs"], name + " sequences")
+        assert_bitexact(out["profit"], full_golden[name + "/profit"], name + " profit")
+        assert_bitexact(out["dd"], full_golden[name + "/dd"], name + " drawdown")
+        ids = full_golden[name + "/rank_ids"]
+        assert_bitexact(out["summary"][ids - 1], full_golden[name + "/rows"], name + " summary rows")
+        rep = oracle.eval_paths(full_golden[name + "/seqs"], num_trades=1000)
+        assert_bitexact(rep["profit"], full_golden[name + "/profit"], name + " replay profit")
+        assert_bitexact(rep["summary"][ids - 1], full_golden[name + "/rows"], name + " replay rows")
+
+
 def test_survey_known_answers(kat):
     """SURVEY.md A.5 hex-exact anchors (independent of the fixture file)."""
     row = lambda name, sid: kat[name + "/rows"][list(kat[name + "/rank_ids"]).index(sid)]

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 3) k_one_pass(const __grid_constant__ Pat
     src.tab = tab;
     src.word = 0;
     __syncthreads();
-    if (active) run_pass<OnePass, PM_FULL, MCTS_SEL_FULL>(src, a, local);
+    if (active) run_pass_k<OnePass, PM_FULL, MCTS_SEL_FULL>(src, a, local);
 }
 }  // namespace mcts
 void launch_one(const mcts::PathArgs &a) { mcts::k_one_pass<<<1, 128>>>(a); }

@@ -22,7 +22,7 @@ static __global__ void __launch_bounds__(128) k_gen_base(const __grid_constant__
 }
 
 // wide runs (more values than 4-bit codes): one thread per path shuffles its fp64 sequence in global
-// memory, values[local][t]; k_replay_pass then evaluates it.  Rare fallback, not tuned.
+// memory, values[local][t]; k_replay_paths then evaluates it.  Rare fallback, not tuned.
 static __global__ void __launch_bounds__(128) k_shuffle_values(const __grid_constant__ PathArgs a, double *__restrict__ values)
 {
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

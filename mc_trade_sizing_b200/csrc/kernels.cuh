@@ -8,7 +8,8 @@
 //                     per-path results go to HBM once (320 B per path = 0.016 B per trade-step).
 //                     MODE: all 20 ids, the 11 distinct behaviours (dedup), or all 20 + equity curves
 //   k_sim_paths_int   the same with the exact int32 evaluator (all-integer runs)
-//   k_replay_pass     the fp64 evaluator on caller-supplied sequences (replay mode), one pass per launch
+//   k_replay_paths    the fp64 evaluator on caller-supplied sequences (replay mode): rows staged through shared memory
+//                     by cp.async in transposed tiles, all passes in one launch
 //   k_sequences       audit hook: the generated sequences as doubles
 // The non-template kernels (k_gen_base, k_reduce_nodes/top, k_shuffle_values, k_peak_*) live in aux_kernels.cuh,
 // which only mcts.cu includes, so they are compiled once and not into every paths_*.cu translation unit.
@@ -90,14 +91,11 @@ struct CurveSink {
     }
 };
 
-template <class IDS, int MODE, int SEL, bool CHECK_FINITE = false, class SRC>
+template <class IDS, int MODE, int SEL, class SRC>
 __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t local)
 {
     double profit[IDS::N], dd[IDS::N];
-    if constexpr (CHECK_FINITE) {  // caller-supplied values (replay): see eval_path
-        NoSink sink;
-        if (eval_path<IDS, SEL, MODE == PM_FULL>(src, sink, a.sched, profit, dd) && a.flags != nullptr) atomicOr(a.flags, 1u);
-    } else if constexpr (MODE == PM_CURVES) {
+    if constexpr (MODE == PM_CURVES) {
         CurveSink<IDS> sink;
         sink.base = reinterpret_cast<double2 *>(a.curves);
         sink.n = a.n;
@@ -109,6 +107,34 @@ __device__ __forceinline__ void run_pass(SRC &src, const PathArgs &a, int64_t lo
         NoSink sink;
         eval_path<IDS, SEL, MODE == PM_FULL>(src, sink, a.sched, profit, dd);  // PM_FULL: 20 separate chains
     }
+    if (a.out == nullptr) return;
+    static_for<IDS::N>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        constexpr int id = IDS::id(s);
+        if constexpr (MODE == PM_DEDUP) {
+#pragma unroll
+            for (int other = 1; other <= kNumStrategies; other++) {
+                if (rule_of_id(other) == rule_of_id(id)) {
+                    a.out[(int64_t)(other - 1) * a.ld + a.out_off + local] = profit[s];
+                    a.out[(int64_t)(kNumStrategies + other - 1) * a.ld + a.out_off + local] = dd[s];
+                }
+            }
+        } else {
+            a.out[(int64_t)(id - 1) * a.ld + a.out_off + local] = profit[s];
+            a.out[(int64_t)(kNumStrategies + id - 1) * a.ld + a.out_off + local] = dd[s];
+        }
+    });
+}
+
+// replay flavour of run_pass: caller-supplied values (finite check), stores only for `store` threads
+template <class IDS, int MODE, class SRC>
+__device__ __forceinline__ void run_pass_replay(SRC &src, const PathArgs &a, int64_t local, bool store)
+{
+    double profit[IDS::N], dd[IDS::N];
+    NoSink sink;
+    const bool nonfinite = eval_path<IDS, MCTS_SEL_REPLAY, MODE == PM_FULL>(src, sink, a.sched, profit, dd);
+    if (!store) return;
+    if (nonfinite && a.flags != nullptr) atomicOr(a.flags, 1u);
     if (a.out == nullptr) return;
     static_for<IDS::N>([&](auto S) {
         constexpr int s = decltype(S)::value;
@@ -260,15 +286,142 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(
     else run_pass_int<FullAll, MODE>(codes + tid, BLOCK, tab, a, local);
 }
 
-// replay: values [n][T] row-major fp64 in device memory, one pass (five strategies) per launch
-template <class IDS, int MODE>
-__global__ void __launch_bounds__(kBlock, kBlocksPerSM) k_replay_pass(const __grid_constant__ PathArgs a, const double *__restrict__ values, int64_t T)
+// ---- replay: the fp64 evaluator on caller-supplied sequences -------------------------------------------------
+// values [n][T] row-major fp64 in device memory.  One thread owns one path, like k_sim_paths, but a thread reading its
+// own row touches 32 different 128-byte lines per warp load (the round-1 kernel: 1.19e12 trade-steps/s, bound by L1
+// tag look-ups).  Here a block of 128 paths streams its rows through shared memory in tiles of kReplayTile trades:
+//   * every warp copies whole row segments -- 32 lanes x 8 bytes = 256 contiguous bytes of ONE path per instruction --
+//     with cp.async (LDGSTS: global -> shared without a register round trip), transposing on the way into
+//     tile[trade][path] with an odd pitch, so that neither the asynchronous writes (lane stride = pitch) nor the
+//     evaluator's reads (lane stride = 1) conflict on shared-memory banks;
+//   * two tiles: the copy of tile k+1 is in flight while tile k is evaluated (one barrier per tile);
+//   * all passes of a mode run inside ONE launch (they re-stream the block's rows, which the previous pass left in L2
+//     when the chunk is small enough), so a chunk is one launch instead of four.
+constexpr int kReplayBlock = 128;
+constexpr int kReplayTile = 32;                    // trades per tile = four 8-trade blocks
+constexpr int kReplayPitch = kReplayBlock + 1;     // doubles per tile row: odd -> conflict-free transposing writes
+constexpr size_t kReplaySmem = 2 * (size_t)kReplayTile * kReplayPitch * sizeof(double);   // 66 KB per block, 3 blocks per SM
+
+struct TileSource {
+    static constexpr bool kSharedLo = false;  // arbitrary caller values
+    const double *rows;   // first row of this block
+    int64_t T;
+    int n_rows;           // valid rows of this block (<= kReplayBlock)
+    int n_tiles;
+    double *tiles;        // [2][kReplayTile][kReplayPitch] in shared memory
+    int tid;
+    double v[8];
+
+    __device__ __forceinline__ void issue(int tile)
+    {
+        if (tile < n_tiles) {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int64_t t = (int64_t)tile * kReplayTile + lane;
+            double *dst = tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)lane * kReplayPitch;
+            if (t < T) {
+                for (int r = warp; r < n_rows; r += kReplayBlock / 32) {
+                    const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + r);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(rows + (int64_t)r * T + t) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // start of a pass: nobody may still be reading the tiles of the previous pass
+    __device__ __forceinline__ void begin_pass()
+    {
+        __syncthreads();
+        issue(0);
+    }
+    // make tile `tile` readable and start the copy of the next one into the other buffer
+    __device__ __forceinline__ void acquire(int tile)
+    {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of `tile` has landed ...
+        __syncthreads();                                      // ... and everybody's; everybody is done with tile - 1
+        issue(tile + 1);
+    }
+    __device__ __forceinline__ const double *slot(int oct) const
+    {
+        const int tile = oct / (kReplayTile / 8), o = oct % (kReplayTile / 8);
+        return tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)(o * 8) * kReplayPitch + tid;
+    }
+    __device__ __forceinline__ uint32_t load(int oct)
+    {
+        if (oct % (kReplayTile / 8) == 0) acquire(oct / (kReplayTile / 8));
+        const double *p = slot(oct);
+        uint32_t W = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = p[(size_t)i * kReplayPitch];
+            W |= (v[i] > 0.0 ? 1u : 0u) << (4 * i);  // win <=> value > 0 (:154)
+        }
+        return W;
+    }
+    __device__ __forceinline__ uint32_t load_tail(int oct, int count, uint32_t *loss_bits)
+    {
+        if (oct % (kReplayTile / 8) == 0) acquire(oct / (kReplayTile / 8));
+        const double *p = slot(oct);
+        uint32_t W = 0, V = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = i < count ? p[(size_t)i * kReplayPitch] : 0.0;
+            W |= ((i < count && v[i] > 0.0) ? 1u : 0u) << (4 * i);
+            V |= (i < count ? 1u : 0u) << (4 * i);
+        }
+        *loss_bits = W ^ V;
+        return W;
+    }
+    template <int I>
+    __device__ __forceinline__ void get(double &v1, double &v2, double &v3) const
+    {
+        v1 = v[I];
+        v2 = mul_rn(v[I], 2.0);
+        v3 = mul_rn(v[I], 3.0);
+    }
+    __device__ __forceinline__ void get_dyn(int i, double &v1, double &v2, double &v3) const
+    {
+        double x = v[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) x = (i == j) ? v[j] : x;
+        v1 = x;
+        v2 = mul_rn(x, 2.0);
+        v3 = mul_rn(x, 3.0);
+    }
+};
+
+// Every thread of a block runs every pass (the tile barriers need all of them): threads beyond the last path of the launch
+// evaluate the block's last valid row again and store nothing.
+template <int MODE>
+__global__ void __launch_bounds__(kReplayBlock, 3) k_replay_paths(const __grid_constant__ PathArgs a, const double *__restrict__ values, int64_t T)
 {
-    const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (local >= a.n) return;
-    ValueSource src;
-    src.row = values + local * T;  // `values` already points at this launch's first path
-    run_pass<IDS, MODE, MCTS_SEL_REPLAY, true>(src, a, local);
+    extern __shared__ __align__(16) double replay_tiles[];
+    const int64_t first = (int64_t)blockIdx.x * kReplayBlock;
+    const int64_t left = a.n - first;
+    TileSource src;
+    src.rows = values + first * T;  // `values` already points at this launch's first path
+    src.T = T;
+    src.n_rows = (int)(left < kReplayBlock ? left : kReplayBlock);
+    src.n_tiles = (int)((T + kReplayTile - 1) / kReplayTile);
+    src.tiles = replay_tiles;
+    src.tid = (int)threadIdx.x < src.n_rows ? (int)threadIdx.x : src.n_rows - 1;
+    const bool active = (int)threadIdx.x < src.n_rows;
+    const int64_t local = first + src.tid;
+    auto pass = [&](auto IDS) {
+        using L = decltype(IDS);
+        src.begin_pass();
+        // inactive threads still walk the pass (barriers); their stores are suppressed by a null output pointer
+        run_pass_replay<L, MODE>(src, a, local, active);
+    };
+    if constexpr (MODE == PM_DEDUP) {
+        pass(DedupPass0{});
+        pass(DedupPass1{});
+        pass(DedupPass2{});
+    } else {
+        pass(FullPass0{});
+        pass(FullPass1{});
+        pass(FullPass2{});
+        pass(FullPass3{});
+    }
 }
 
 template <int K, bool GLOBAL = false>

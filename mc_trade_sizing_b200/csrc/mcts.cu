@@ -67,6 +67,7 @@ struct mcts_handle {
     LeafSched *d_sched = nullptr;
     int64_t sched_L = -1;
     uint32_t *d_flags = nullptr;  // replay: non-finite equity / profit seen (kernels.cuh PathArgs::flags)
+    bool replay_attr[2] = {false, false};  // dynamic shared-memory limit of k_replay_paths<FULL / DEDUP> raised on this device
     // replay: two staging areas for caller sequences (chunk c+1 is copied while chunk c is evaluated)
     double *d_values[2] = {nullptr, nullptr};
     int64_t cap_values[2] = {0, 0};
@@ -448,22 +449,22 @@ static int launch_paths(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
     return MCTS_OK;
 }
 
-// the evaluator passes over fp64 sequences values[a.n][T] already on the device
-static void launch_replay_passes(mcts_handle *h, cudaStream_t stream, int mode, const PathArgs &a, const double *values, int64_t T)
+// the evaluator over fp64 sequences values[a.n][T] already on the device: one launch, all passes (kernels.cuh k_replay_paths)
+static int launch_replay_passes(mcts_handle *h, cudaStream_t stream, int mode, const PathArgs &a, const double *values, int64_t T)
 {
-    const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
-    if (mode == PM_DEDUP) {
-        k_replay_pass<DedupPass0, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
-        k_replay_pass<DedupPass1, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
-        k_replay_pass<DedupPass2, PM_DEDUP><<<grid, kBlock, 0, stream>>>(a, values, T);
-        h->timing.launches += 3;
-    } else {
-        k_replay_pass<FullPass0, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
-        k_replay_pass<FullPass1, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
-        k_replay_pass<FullPass2, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
-        k_replay_pass<FullPass3, PM_FULL><<<grid, kBlock, 0, stream>>>(a, values, T);
-        h->timing.launches += 4;
+    bool *attr_set = h->replay_attr;  // function attributes are per device: remembered per handle
+    const unsigned grid = (unsigned)((a.n + kReplayBlock - 1) / kReplayBlock);
+    const int m = mode == PM_DEDUP ? 1 : 0;
+    if (!attr_set[m]) {  // 66 KB of dynamic shared memory per block
+        CUDA_TRY(m ? cudaFuncSetAttribute(k_replay_paths<PM_DEDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmem)
+                   : cudaFuncSetAttribute(k_replay_paths<PM_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmem));
+        attr_set[m] = true;
     }
+    if (m) k_replay_paths<PM_DEDUP><<<grid, kReplayBlock, kReplaySmem, stream>>>(a, values, T);
+    else k_replay_paths<PM_FULL><<<grid, kReplayBlock, kReplaySmem, stream>>>(a, values, T);
+    CUDA_TRY(cudaGetLastError());
+    h->timing.launches += 1;
+    return MCTS_OK;
 }
 
 // Runs with more distinct values than 4-bit codes can name: shuffle fp64 sequences in global memory,
@@ -483,8 +484,7 @@ static int launch_wide(mcts_handle *h, Lane &L, int mode, const PathArgs &a)
         b.out_off = a.out_off + off;
         k_shuffle_values<<<(unsigned)((b.n + 127) / 128), 128, 0, L.stream>>>(b, h->d_values[0]);
         h->timing.launches++;
-        launch_replay_passes(h, L.stream, mode, b, h->d_values[0], a.g.L);
-        CUDA_TRY(cudaGetLastError());
+        if ((rc = launch_replay_passes(h, L.stream, mode, b, h->d_values[0], a.g.L))) return rc;
     }
     return MCTS_OK;
 }
@@ -689,8 +689,7 @@ int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, cons
         a.ld = L.cap_paths;
         a.flags = h->d_flags;
         if ((rc = mark(h, L.stream, h->ev_paths, true))) return rc;
-        launch_replay_passes(h, h->stream, mode, a, d_vals, T);
-        CUDA_TRY(cudaGetLastError());
+        if ((rc = launch_replay_passes(h, h->stream, mode, a, d_vals, T))) return rc;
         if ((rc = mark(h, L.stream, h->ev_paths, false))) return rc;
         CUDA_TRY(cudaEventRecord(h->values_free[c % n_buf], h->stream));
         if ((rc = launch_reduce(h, L, n, f, h->d_recs + c))) return rc;

@@ -114,3 +114,24 @@ def test_parameter_validation_mirrors_numpy():
     assert lib.mcts_sequence_length(C.byref(make_params(1.3, 1.0, 1.0, 10, 2, 2))) == _ffi.EINVAL   # p > 1 in choice()
     assert b"ValueError" in lib.mcts_last_error()
     assert lib.mcts_sequence_length(C.byref(make_params(1.3, 1.0, 1.0, 10, 2, 2, use_markov=True))) == 10  # rand() < p never validates
+
+
+def test_simulate_refuses_sums_beyond_dbl_max():
+    """3 * max|value| * trades must stay finite, otherwise inf - inf = NaN could arise in the drawdown, which
+    the reference reports (np.min propagates NaN) and the kernels' ordered comparisons would drop."""
+    lib = _ffi.lib()
+    assert lib.mcts_sequence_length(C.byref(make_params(0.5, 1e304, 1e304, 1000, 2, 2))) == 1000      # 3e307: fine
+    assert lib.mcts_sequence_length(C.byref(make_params(0.5, 1e305, 1e305, 1000, 2, 2))) == _ffi.EUNSUPPORTED
+    assert b"DBL_MAX" in lib.mcts_last_error()
+    assert lib.mcts_sequence_length(C.byref(make_params(0.5, 1e305, 1e305, 10, 2, 2))) == 10
+
+
+def test_group_api_needs_a_device_too():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mc_trade_sizing_b200 import EngineGroup
+    for devices in (None, [0], [0, 1]):
+        with pytest.raises(_ffi.MctsError) as e:
+            EngineGroup(devices)
+        assert e.value.code == _ffi.ENODEVICE

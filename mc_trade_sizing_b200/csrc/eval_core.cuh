@@ -69,21 +69,21 @@ struct IdList {
 // body: the lists below are the best of a search (tools/pass_search) scored by the SASS instruction count of
 // the loop bodies and confirmed on the B200.
 #ifndef MCTS_FP0
-#define MCTS_FP0 3, 18, 11, 1, 12
+#define MCTS_FP0 9, 10, 6, 15, 7
 #define MCTS_FP1 14, 4, 5, 8, 17
-#define MCTS_FP2 6, 7, 19, 16, 20
-#define MCTS_FP3 13, 9, 15, 2, 10
+#define MCTS_FP2 3, 18, 1, 12, 11
+#define MCTS_FP3 2, 16, 19, 20, 13
 #endif
 using FullPass0 = IdList<MCTS_FP0>;
 using FullPass1 = IdList<MCTS_FP1>;
 using FullPass2 = IdList<MCTS_FP2>;
 using FullPass3 = IdList<MCTS_FP3>;
 // one representative per behaviour class (results fanned out by the caller); composition and order from
-// the same search (with predicated moves and one head select: 14.65 -> 13.37 ms per 2.1 M paths)
+// the same search (re-run in round 2 for the structure-of-arrays value table: SASS 1246 -> 1135 instructions per 8 trades)
 #ifndef MCTS_DP0
-#define MCTS_DP0 18, 4, 1
-#define MCTS_DP1 9, 8, 16, 6
-#define MCTS_DP2 11, 20, 2, 19
+#define MCTS_DP0 8, 16, 9
+#define MCTS_DP1 6, 1, 2
+#define MCTS_DP2 4, 18, 20, 11, 19
 #endif
 using DedupPass0 = IdList<MCTS_DP0>;
 using DedupPass1 = IdList<MCTS_DP1>;
@@ -305,14 +305,25 @@ MCTS_HD void acc_init(Acc<IDS::N> &a)
 // saturated port).  The multiplier 1 and addend 0 come from constant memory so that ptxas cannot
 // fold the multiply-add into a move (which it would turn back into selects).
 static __constant__ uint32_t c_sel_one = 1u, c_sel_zero = 0u;
+template <bool INT_SIGN>
 __device__ __forceinline__ void psel_gt0(double &dst, double u, double src)
 {
-    asm("{ .reg .pred p; .reg .b32 lo, hi, slo, shi;\n\t"
-        "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
-        "mov.b64 {lo,hi}, %0;\n\tmov.b64 {slo,shi}, %2;\n\t"
-        "@p mad.lo.u32 lo, slo, %3, %4;\n\t@p mad.lo.u32 hi, shi, %3, %4;\n\t"
-        "mov.b64 %0, {lo,hi}; }"
-        : "+d"(dst) : "d"(u), "d"(src), "r"(c_sel_one), "r"(c_sel_zero));
+    if constexpr (INT_SIGN) {  // u > 0 as a signed test of the high word (see trade_step): ALU pipe instead of FP64
+        asm("{ .reg .pred p; .reg .b32 lo, hi, slo, shi, ulo, uhi;\n\t"
+            "mov.b64 {ulo,uhi}, %1;\n\t"
+            "setp.gt.s32 p, uhi, 0;\n\t"
+            "mov.b64 {lo,hi}, %0;\n\tmov.b64 {slo,shi}, %2;\n\t"
+            "@p mad.lo.u32 lo, slo, %3, %4;\n\t@p mad.lo.u32 hi, shi, %3, %4;\n\t"
+            "mov.b64 %0, {lo,hi}; }"
+            : "+d"(dst) : "d"(u), "d"(src), "r"(c_sel_one), "r"(c_sel_zero));
+    } else {
+        asm("{ .reg .pred p; .reg .b32 lo, hi, slo, shi;\n\t"
+            "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+            "mov.b64 {lo,hi}, %0;\n\tmov.b64 {slo,shi}, %2;\n\t"
+            "@p mad.lo.u32 lo, slo, %3, %4;\n\t@p mad.lo.u32 hi, shi, %3, %4;\n\t"
+            "mov.b64 %0, {lo,hi}; }"
+            : "+d"(dst) : "d"(u), "d"(src), "r"(c_sel_one), "r"(c_sel_zero));
+    }
 }
 __device__ __forceinline__ void psel_lt(double &dst, double u)
 {
@@ -325,8 +336,29 @@ __device__ __forceinline__ void psel_lt(double &dst, double u)
 }
 #endif
 
-// SEL: bit 0 = peak, bit 1 = drawdown updated by predicated IMAD moves (device only); 0 = plain selects
-template <int SEL = 0>
+// SEL: bit 0 = peak, bit 1 = drawdown updated by predicated IMAD moves (device only); 0 = plain selects.
+// INT_SIGN: decide "u > 0" (new equity peak) by a signed integer test of u's HIGH WORD (ISETP, ALU pipe) instead of an
+// fp64 compare (DSETP, FP64 pipe -- the busiest pipe of the kernel).  The two agree for every double except positive
+// subnormals (high word 0, low word != 0) and NaN.  The categorical kernels may use it: build_spec admits only trade
+// values that are 0 or at least 2^-969 in magnitude, so every contribution, equity and equity difference is an integer
+// multiple of 2^-1021 -- never a non-zero subnormal -- and it bounds the sums so that no NaN can arise.  The replay
+// kernels (arbitrary caller values) keep the fp64 compare.
+// MEASURED SLOWER on the B200 and therefore OFF: k_sim_paths 20.02 ms with the integer test against 19.76 ms with DSETP
+// (each with its own searched pass lists, same SASS length) -- the FP64 pipe at 58 % is not what holds the kernel back,
+// the extra ALU-pipe instruction is.  Kept as a compile-time switch with its tests, not shipped.
+#ifndef MCTS_INT_SIGN
+#define MCTS_INT_SIGN 0
+#endif
+MCTS_HD bool gt_zero_hi(double u)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(u) > 0;
+#else
+    return u > 0.0;
+#endif
+}
+
+template <int SEL = 0, bool INT_SIGN = false>
 MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double c)
 {
     E = E + c;
@@ -334,7 +366,8 @@ MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double 
     const double u = E - peak;
 #if defined(__CUDA_ARCH__)
     // peak before drawdown: the other order costs ptxas ~2 more register moves per step
-    if constexpr ((SEL & 1) != 0) psel_gt0(peak, u, E); else peak = (u > 0.0) ? E : peak;
+    if constexpr ((SEL & 1) != 0) psel_gt0<INT_SIGN>(peak, u, E);
+    else peak = (INT_SIGN ? gt_zero_hi(u) : (u > 0.0)) ? E : peak;
     if constexpr ((SEL & 2) != 0) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
 #else
     peak = (u > 0.0) ? E : peak;
@@ -367,7 +400,7 @@ MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t
             // ptxas turns the predicated moves of the first trades of a loop body into copy + select (the state
             // crosses the back edge); plain selects cost the same there and need no copies
             // (SEL >> 2 = how many leading trades of the block use plain selects)
-            trade_step<(i < (SEL >> 2) ? 0 : (SEL & 3))>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
+            trade_step<(i < (SEL >> 2) ? 0 : (SEL & 3)), SRC::kIntSign>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     });
@@ -387,7 +420,7 @@ MCTS_HD void eval_tail(Acc<IDS::N> &a, double (&res)[IDS::N], uint32_t W, uint32
             constexpr int s = decltype(S)::value;
             constexpr int rule = rule_of_id(IDS::id(s));
             const double c = contribution<rule, SRC::kSharedLo>(p, v1, v2, v3);
-            trade_step<(SEL & 3)>(a.E[s], a.peak[s], a.dd[s], res[s], c);
+            trade_step<(SEL & 3), SRC::kIntSign>(a.E[s], a.peak[s], a.dd[s], res[s], c);
             sink.template put<s>(t0 + i, a.E[s]);
         });
     }
@@ -623,6 +656,7 @@ MCTS_HD void tab_get(const TabSoA *tab, uint32_t code, double &v1, double &v2, d
 template <class TAB>
 struct CodeSourceT {
     static constexpr bool kSharedLo = true;  // build_spec rejects subnormal / overflowing values
+    static constexpr bool kIntSign = MCTS_INT_SIGN != 0;  // ... and values below 2^-969: see trade_step
     const uint32_t *codes;  // word of block `oct` at codes[oct * stride]
     int stride;
     const TAB *tab;
@@ -665,6 +699,7 @@ MCTS_HD double mul_rn(double a, double b)
 // replay: arbitrary fp64 trade results of one path, contiguous in memory
 struct ValueSource {
     static constexpr bool kSharedLo = false;  // arbitrary caller values
+    static constexpr bool kIntSign = false;
     const double *row;
     double v[8];
     MCTS_HD uint32_t load(int oct)

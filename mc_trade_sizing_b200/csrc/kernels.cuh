@@ -304,18 +304,20 @@ constexpr size_t kReplaySmem = 2 * (size_t)kReplayTile * kReplayPitch * sizeof(d
 
 struct TileSource {
     static constexpr bool kSharedLo = false;  // arbitrary caller values
+    static constexpr bool kIntSign = false;
     const double *rows;   // first row of this block
     int64_t T;
     int n_rows;           // valid rows of this block (<= kReplayBlock)
     int n_tiles;
     double *tiles;        // [2][kReplayTile][kReplayPitch] in shared memory
-    int tid;
+    int tid;              // the row this thread EVALUATES (clamped to the last valid row of the block)
+    int copy_tid;         // threadIdx.x: this thread's place in the cooperative copy
     double v[8];
 
     __device__ __forceinline__ void issue(int tile)
     {
         if (tile < n_tiles) {
-            const int lane = tid & 31, warp = tid >> 5;
+            const int lane = copy_tid & 31, warp = copy_tid >> 5;
             const int64_t t = (int64_t)tile * kReplayTile + lane;
             double *dst = tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)lane * kReplayPitch;
             if (t < T) {
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(kReplayBlock, 3) k_replay_paths(const __grid_c
     src.n_tiles = (int)((T + kReplayTile - 1) / kReplayTile);
     src.tiles = replay_tiles;
     src.tid = (int)threadIdx.x < src.n_rows ? (int)threadIdx.x : src.n_rows - 1;
+    src.copy_tid = (int)threadIdx.x;
     const bool active = (int)threadIdx.x < src.n_rows;
     const int64_t local = first + src.tid;
     auto pass = [&](auto IDS) {

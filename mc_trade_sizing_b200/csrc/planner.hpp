@@ -157,8 +157,10 @@ inline int build_spec(const mcts_params &p, GenSpec *out, std::string *err)
             const double v = g.val[k];
             const int win = v > 0;
             const int idx = win ? n_win++ : n_loss++;
-            if (v != 0.0 && !(fabs(v) >= 4.450147717014403e-308 && fabs(v) <= 8.98846567431158e+307)) {
-                *err = "trade values must be 0 or between 2^-1021 and 2^1023 in magnitude in simulate mode (use replay for such inputs)";
+            // >= 2^-969: every equity difference is then a multiple of 2^-1021, i.e. never a non-zero subnormal, which lets the
+            // kernels test "new peak" on the high word alone (eval_core.cuh trade_step) and share the low word of v and 2v
+            if (v != 0.0 && !(fabs(v) >= 2.004168360008973e-292 && fabs(v) <= 8.98846567431158e+307)) {
+                *err = "trade values must be 0 or between 2^-969 and 2^1023 in magnitude in simulate mode (use replay for such inputs)";
                 return MCTS_EUNSUPPORTED;
             }
             if (g.wide) {

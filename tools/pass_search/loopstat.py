@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Instruction count of the 8-trade loop bodies of k_sim_paths in a cubin (cuobjdump -sass): for every innermost
-backward branch whose body holds 16 x NS DSETPs and no local-memory traffic, the body length and NS.
+backward branch whose body holds 24 x NS DADDs (three per trade-step) and no local-memory traffic, the body length and NS.
     python tools/pass_search/loopstat.py file.cubin"""
 import re
 import subprocess
@@ -20,9 +20,9 @@ def loop_bodies(cubin):
         if not m or int(m.group(1), 16) >= addr:
             continue
         seg = [t for a, t in ins if int(m.group(1), 16) <= a <= addr]
-        n_dsetp = sum("DSETP" in t for t in seg)
-        if n_dsetp >= 48 and n_dsetp % 16 == 0 and not any(t.startswith(("LDL", "STL")) for t in seg):
-            bodies.append((len(seg), n_dsetp // 16))   # instructions per 8 trades, strategies in the pass
+        n_dadd = sum(re.sub(r"^@!?U?P\d+\s+", "", t).startswith("DADD") for t in seg)   # 3 per trade-step
+        if n_dadd >= 72 and n_dadd % 24 == 0 and not any(t.startswith(("LDL", "STL")) for t in seg):
+            bodies.append((len(seg), n_dadd // 24))   # instructions per 8 trades, strategies in the pass
     return bodies
 
 

@@ -74,6 +74,18 @@ struct IdList {
 #define MCTS_FP2 3, 18, 1, 12, 11
 #define MCTS_FP3 2, 16, 19, 20, 13
 #endif
+// the replay kernel (caller-supplied values, kernels.cuh k_replay_paths) evaluates the same ids with a different value source;
+// its loop bodies are allocated differently by ptxas, so it has pass lists of its own from the same search
+#ifndef MCTS_RP0
+#define MCTS_RP0 MCTS_FP0
+#define MCTS_RP1 MCTS_FP1
+#define MCTS_RP2 MCTS_FP2
+#define MCTS_RP3 MCTS_FP3
+#endif
+using ReplayPass0 = IdList<MCTS_RP0>;
+using ReplayPass1 = IdList<MCTS_RP1>;
+using ReplayPass2 = IdList<MCTS_RP2>;
+using ReplayPass3 = IdList<MCTS_RP3>;
 using FullPass0 = IdList<MCTS_FP0>;
 using FullPass1 = IdList<MCTS_FP1>;
 using FullPass2 = IdList<MCTS_FP2>;
@@ -113,8 +125,10 @@ constexpr bool rules_distinct()
 }
 constexpr bool full_passes_cover_all_ids()
 {
-    for (int id = 1; id <= 20; id++)
+    for (int id = 1; id <= 20; id++) {
         if (count_id<FullPass0>(id) + count_id<FullPass1>(id) + count_id<FullPass2>(id) + count_id<FullPass3>(id) != 1) return false;
+        if (count_id<ReplayPass0>(id) + count_id<ReplayPass1>(id) + count_id<ReplayPass2>(id) + count_id<ReplayPass3>(id) != 1) return false;
+    }
     return true;
 }
 constexpr bool dedup_passes_cover_all_rules()

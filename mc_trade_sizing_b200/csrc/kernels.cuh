@@ -420,10 +420,10 @@ __global__ void __launch_bounds__(kReplayBlock, 3) k_replay_paths(const __grid_c
         pass(DedupPass1{});
         pass(DedupPass2{});
     } else {
-        pass(FullPass0{});
-        pass(FullPass1{});
-        pass(FullPass2{});
-        pass(FullPass3{});
+        pass(ReplayPass0{});
+        pass(ReplayPass1{});
+        pass(ReplayPass2{});
+        pass(ReplayPass3{});
     }
 }
 

@@ -46,19 +46,43 @@ def bytes_to_records(buf: np.ndarray, n: int):
     return recs
 
 
+_PINNED = {}
+
+
+def _pinned(nbytes: int, tag: str):
+    """Reusable pinned host staging buffers (the exchange is a few KB; allocation would dominate it)."""
+    import torch
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        _PINNED[tag] = buf
+    return buf[:nbytes]
+
+
 def gather_records(local_bytes: np.ndarray, counts, rank: int, world: int, device=None, group=None) -> np.ndarray:
     """all_gather of the per-rank record blocks (padded to the largest block); returns the
-    concatenation in rank order.  `device` None -> CPU tensors (gloo), else CUDA tensors (NCCL)."""
+    concatenation in rank order.  `device` None -> CPU tensors (gloo), else CUDA tensors (NCCL): pinned staging
+    buffers, asynchronous copies on the current stream and ONE synchronisation, after the gathered block is back."""
     import torch
     import torch.distributed as dist
-    width = max(counts) * REC_BYTES
-    send = torch.zeros(width, dtype=torch.uint8)
-    send[: local_bytes.size] = torch.from_numpy(local_bytes)
-    if device is not None:
-        send = send.to(device)
-    recv = torch.empty(world * width, dtype=torch.uint8, device=send.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    host = recv.cpu().numpy().reshape(world, width)
+    width = max(max(counts) * REC_BYTES, 1)
+    if device is None:
+        send = torch.zeros(width, dtype=torch.uint8)
+        send[: local_bytes.size] = torch.from_numpy(local_bytes)
+        recv = torch.empty(world * width, dtype=torch.uint8)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        host = recv.numpy().reshape(world, width)
+    else:
+        stage = _pinned(width, "send")
+        stage.zero_()
+        stage[: local_bytes.size] = torch.from_numpy(local_bytes)
+        send = stage.to(device, non_blocking=True)
+        recv = torch.empty(world * width, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        back = _pinned(world * width, "recv")
+        back.copy_(recv, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        host = back.numpy().reshape(world, width)
     return np.concatenate([host[r, : counts[r] * REC_BYTES] for r in range(world)])
 
 

@@ -43,6 +43,10 @@ if not a.skip_c5:
 
 eng = Engine(local)
 eng.simulate(make_params(0.82, 186.0, 219.0, 1000, 1000, 20))  # warm-up: context, buffers
+if world > 1:  # ... and the communicator: the first NCCL collective of a process group takes ~1 s (it used to land in C1's wall time)
+    wp = make_params(0.82, 186.0, 219.0, 1000, 4096 * world, 20)
+    wch = mdist.resolve_chunk(4096 * world * 20, 0, world)
+    mdist.simulate_sharded(wp, 1, lambda lo, hi: eng.simulate_chunks(wp, 1, lo, hi, options=eng.options(chunk_paths=wch)), rank, world, chunk_paths=wch, device=device)
 if rank == 0:
     print("%d GPU(s)" % world)
 for name, args, kw, expect in CONFIGS:

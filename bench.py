@@ -32,7 +32,7 @@ CHUNK_PATHS = 1 << 22          # the library default: two 4.19 M-path chunks per
 METRIC = "trade-steps/sec (paths x trades x strategies)"
 UNIT = "trade-steps/s"
 FP64_OPS_PER_TRADE_STEP = 6          # mul, add(equity), max, sub, min, add(profit)
-TRAFFIC_PER_LAUNCH = 642.2e6         # dram bytes read + written by one k_sim_paths launch: a CONSTANT from the committed
+TRAFFIC_PER_LAUNCH = 645.3e6         # dram bytes read + written by one k_sim_paths launch: a CONSTANT from the committed ncu capture
 TRAFFIC_SOURCE = "ncu constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r02_ncu_bench_sim_paths.txt (not re-measured by bench.py)"
 C5_FULL_SIMS = 50_000_000            # x 20 shuffles = 1e9 paths: BASELINE.json config 5 at its stated size
 STRONG_SIMS = 3_355_456              # x 20 = 67,109,120 paths: the FIXED problem of the strong-scaling line (8 x the per-GPU batch)

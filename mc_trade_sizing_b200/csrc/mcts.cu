@@ -377,6 +377,9 @@ cudaError_t mcts_launch_paths_int_dedup(const PathArgs &a, int block, cudaStream
 // (mcts_options.block_threads) overrides for experiments.
 static int pick_block(int L, int want)
 {
+#ifdef MCTS_BLOCK192
+    if (want == 192 && path_smem_bytes(L, 192) * 2 <= 227 * 1024) return 192;
+#endif
     const int cands[3] = {128, 64, 32};
     int resident[3] = {0, 0, 0}, best = 0;
     for (int i = 0; i < 3; i++) {

@@ -27,6 +27,9 @@ static cudaError_t launch_k(const PathArgs &a, int block, cudaStream_t stream)
         case 128: return launch_kb<K, MODE, 128>(a, stream);
         case 64: return launch_kb<K, MODE, 64>(a, stream);
         case 32: return launch_kb<K, MODE, 32>(a, stream);
+#ifdef MCTS_BLOCK192   // experiment: two 192-thread blocks per SM (mcts_options.block_threads = 192)
+        case 192: return launch_kb<K, MODE, 192>(a, stream);
+#endif
     }
     return cudaErrorInvalidValue;
 }

@@ -168,6 +168,44 @@ def python_reference_rates(cores=None):
         return {"unavailable": "python reference run failed: %r" % (e,)}
 
 
+def dps_overlay_walls():
+    """The reference's UNCHANGED orchestrator (`python dps.py`: 12 CLI subprocesses, three at a time, its shipped
+    dps_config.yaml = 12 x 4,000 paths x 1,000 trades x 20 = 9.6e8 trade-steps, scrape, sinks) against the drop-in through
+    the overlay of INTEGRATION.md section 3 -- directly (12 CUDA contexts) and through the engine daemon (MCTS_SERVER=1).
+    Uses the test helper tests/dps_overlay.py and the stand-ins for openpyxl / influxdb_client / flask under tests/stubs."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import dps_overlay
+    except Exception as e:
+        return {"unavailable": "tests/dps_overlay.py not importable: %r" % (e,)}
+    ref = dps_overlay.reference_dir()
+    if ref is None:
+        return {"unavailable": "no reference copy (baseline/_ref) on this box"}
+    out = {"runs": 12, "trade_steps": 960000000, "reference_wall_s_estimate": 9.6e8 / 5.0e6,
+           "reference_estimate_note": "9.6e8 trade-steps at the three-process rate of cpu_baseline.python_reference (~5e6/s): about 3-5 min"}
+    tmp = tempfile.mkdtemp(prefix="mcts_dps_")
+    try:
+        for name, served in (("direct", False), ("daemon", True)):
+            ov = dps_overlay.build_overlay(os.path.join(tmp, name), ref)
+            sdir = os.path.join(tmp, name + "-server")
+            env = dict(MCTS_SERVER="1", MCTS_SERVER_DIR=sdir, MCTS_SERVER_SOCKET=os.path.join(sdir, "server.sock"), MCTS_SERVER_IDLE="30") if served else {"MCTS_SERVER": "0"}
+            t0 = time.perf_counter()
+            p = dps_overlay.run_dps(ov, extra_env=env, timeout=600)
+            wall = time.perf_counter() - t0
+            rows = len(dps_overlay.check_outputs(ov)) if p.returncode == 0 else 0
+            out[name] = {"wall_s": wall, "returncode": p.returncode, "scraped_rows": rows}
+            if served:
+                subprocess.run([sys.executable, "-m", "mc_trade_sizing_b200.server", "--stop"], env=dict(os.environ, PYTHONPATH=ROOT, **env), cwd=ROOT,
+                               capture_output=True, timeout=30)
+    except Exception as e:
+        out["error"] = repr(e)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU path on the box's host cores (all threads), same
     metric / config.  Rank 0 alone runs it."""
@@ -530,6 +568,8 @@ def main():
     if not args.no_cpu_baseline and n_gpus == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate().items() if k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["python_reference"] = python_reference_rates()
+    if not args.no_extras and n_gpus == 1:
+        line["dps_py_unchanged"] = dps_overlay_walls()
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

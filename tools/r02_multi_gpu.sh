@@ -1,12 +1,12 @@
 #!/bin/bash
-# Round-2 GPU session 4 (N B200s, N = number visible): GPU tests incl. the multi-device group on every GPU, the N-GPU bench
+# Round-2 multi-GPU evidence (N B200s, N = number visible; gpurun --gpus N -- "bash tools/r02_multi_gpu.sh [grouptests|notests]"): GPU tests incl. the multi-device group on every GPU, the N-GPU bench
 # line (torchrun), BASELINE's five configs at full size over N ranks, and the same through ONE process (MCTS_DEVICES=all).
 set -x
 R=r02
 N=$(nvidia-smi -L | wc -l)
 mkdir -p gpurun_out
 if [ "$1" == "grouptests" ]; then   # only the multi-device tests (an 8-GPU box is charged eight-fold)
-  timeout 900 python -m pytest tests/test_gpu_round2.py -m gpu -x -q -s -k "group or device_list" > gpurun_out/${R}_tests_${N}gpu.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${R}_tests_${N}gpu.log
+  timeout 900 python -m pytest tests/test_gpu_round2.py -m gpu -x -q -s -k "group or device_list or nccl" > gpurun_out/${R}_tests_${N}gpu.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${R}_tests_${N}gpu.log
   tail -6 gpurun_out/${R}_tests_${N}gpu.log
 elif [ "$1" != "notests" ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/${R}_tests_${N}gpu.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${R}_tests_${N}gpu.log

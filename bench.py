@@ -542,6 +542,13 @@ def main():
         # (DESIGN.md section 5), so it is no longer bounded by this figure -- kept as a reference point
         "mix_ceiling": {"strategy_steps_per_s": peaks["step_ceiling_per_s"], "kernel_frac": kernel_rate / peaks["step_ceiling_per_s"],
                         "note": "select-based replica (ALU-pipe bound); the kernel uses FMA-pipe predicated moves instead"},
+        # register-only loop with the shipped step's instruction mix (5 DADD + 4 IMAD + 4 LOP3 per strategy-step, independent chains) at
+        # the kernel's occupancy, measured in this process (mcts_measure_mix_ceiling): what the schedulers can issue for this mix
+        "issue_mix_ceiling": {"strategy_steps_per_s": peaks["mix_ceiling_per_s"], "ipc_per_scheduler": peaks["mix_ceiling_ipc"],
+                              "kernel_frac": kernel_rate / peaks["mix_ceiling_per_s"],
+                              "note": "13 instructions per step in the replica (ptxas schedules it D F D A ...: an fp64 instruction in every other "
+                                      "slot), ~13.5 in the kernel incl. generation; the same mix in ptxas' clustered schedule issues 0.845 "
+                                      "(profiles/r02_pipe_mix_bench.txt); the kernel's own IPC is 0.78 (profiles/r02_ncu_bench_sim_paths.txt)"},
         "hbm_note": "aggregate mode moves 0.016 B per trade-step (per-path results only); HBM bounds only curve export",
     }
 

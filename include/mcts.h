@@ -239,6 +239,11 @@ int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst
  * occupancy: the ceiling of this instruction mix on the chip (no generator, no memory). */
 int mcts_measure_step_ceiling(mcts_handle *h, double *strategy_steps_per_s);
 
+/* Rate (strategy-steps/s) and instructions per cycle and scheduler of a register-only loop with the instruction MIX of the
+ * shipped evaluator's trade step (5 fp64 adds + 4 integer multiply-adds + 4 logic operations per step, independent chains)
+ * at the hot kernel's occupancy: what the schedulers can issue for this mix -- the practical ceiling of the issue roofline. */
+int mcts_measure_mix_ceiling(mcts_handle *h, double *strategy_steps_per_s, double *ipc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,7 @@ PROTOTYPES = [
     ("mcts_get_stream", C.c_void_p, [C.c_void_p]),
     ("mcts_measure_peaks", C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     ("mcts_measure_step_ceiling", C.c_int, [C.c_void_p, _dp]),
+    ("mcts_measure_mix_ceiling", C.c_int, [C.c_void_p, _dp, _dp]),
 ]
 
 _lib = None

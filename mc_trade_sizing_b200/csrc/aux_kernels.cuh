@@ -275,4 +275,40 @@ static __global__ void __launch_bounds__(128, 3) k_peak_step(double *out, int st
     if (steps8 < 0) out[0] = acc;
 }
 
+// Register-only loop with the INSTRUCTION MIX of the shipped evaluator's trade step -- per step 5 fp64 adds (FP64 pipe), 4 integer
+// multiply-adds (FMA-heavy pipe, where the predicated moves run) and 4 logic operations (ALU pipe), every instruction on its own
+// dependency chain, interleaved -- at the hot kernel's occupancy (128-thread blocks, three per SM).  What the chip's schedulers can
+// issue for this mix with no generator, no shared memory, no data dependence between neighbours: the practical ceiling of the issue
+// roofline (tools/pipe_mix_bench.cu sweeps other mixes and occupancies; profiles/r02_pipe_mix_bench.txt).
+static __global__ void __launch_bounds__(128, 3) k_peak_mix(double *out, int steps, double x, unsigned y, unsigned z)
+{
+    double d[5];
+    unsigned f[4], a[4];
+#pragma unroll
+    for (int i = 0; i < 5; i++) d[i] = threadIdx.x + i;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f[i] = threadIdx.x * 3 + i;
+        a[i] = threadIdx.x * 5 + i;
+    }
+    for (int it = 0; it < steps; it += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(x));
+                if (i < 4) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(f[i]) : "r"(y));
+                if (i < 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x1e;" : "+r"(a[i]) : "r"(y), "r"(z));
+            }
+        }
+    }
+    double s = 0;
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) s += d[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) t ^= f[i] ^ a[i];
+    if (s == 1.2345e-300 && t == 0x12345u) out[0] = s;
+}
+
 }  // namespace mcts

@@ -862,6 +862,37 @@ int mcts_measure_step_ceiling(mcts_handle *h, double *strategy_steps_per_s)
     return MCTS_OK;
 }
 
+int mcts_measure_mix_ceiling(mcts_handle *h, double *strategy_steps_per_s, double *ipc)
+{
+    if (!h || !strategy_steps_per_s) return fail(MCTS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 3 * 4, steps = 40000, per_step = 13;
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 64));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    float ms = 0;
+    for (int rep = 0; rep < 3; rep++) {  // last repetition counts
+        CUDA_TRY(cudaEventRecord(a, h->stream));
+        k_peak_mix<<<blocks, 128, 0, h->stream>>>(d_out, steps, 1.0000001, 0x9e3779b9u, 0x7f4a7c15u);
+        CUDA_TRY(cudaEventRecord(b, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    }
+    const double warp_steps = (double)blocks * 4 * steps;  // one "strategy-step" of a warp = 13 instructions
+    *strategy_steps_per_s = warp_steps * 32.0 / (ms * 1e-3);
+    if (ipc) {
+        int khz = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+        *ipc = warp_steps * per_step / ((double)h->sm_count * 4.0 * ms * 1e-3 * khz * 1e3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    return MCTS_OK;
+}
+
 int mcts_measure_peaks(mcts_handle *h, double *fp64_inst_per_s, double *int_inst_per_s, double *sm_clock_mhz)
 {
     if (!h) return fail(MCTS_EINVAL, "NULL handle");

@@ -217,7 +217,10 @@ class Engine:
         _raise(lib().mcts_measure_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)))
         d = C.c_double()
         _raise(lib().mcts_measure_step_ceiling(self._h, C.byref(d)))
-        return {"fp64_inst_per_s": a.value, "int_inst_per_s": b.value, "sm_clock_mhz": c.value, "step_ceiling_per_s": d.value}
+        e, f = C.c_double(), C.c_double()
+        _raise(lib().mcts_measure_mix_ceiling(self._h, C.byref(e), C.byref(f)))
+        return {"fp64_inst_per_s": a.value, "int_inst_per_s": b.value, "sm_clock_mhz": c.value, "step_ceiling_per_s": d.value,
+                "mix_ceiling_per_s": e.value, "mix_ceiling_ipc": f.value}
 
 
 class EngineGroup:

@@ -372,17 +372,36 @@ MCTS_HD bool gt_zero_hi(double u)
 #endif
 }
 
+// MCTS_STEP_ORDER / MCTS_NEST: source-order experiments (the arithmetic is the same; ptxas' schedule and register allocation are
+// not).  0 / 0 is what ships; the others were timed with tools/autotune and were not faster.
+#ifndef MCTS_STEP_ORDER
+#define MCTS_STEP_ORDER 0
+#endif
+#ifndef MCTS_NEST
+#define MCTS_NEST 0
+#endif
 template <int SEL = 0, bool INT_SIGN = false>
 MCTS_HD void trade_step(double &E, double &peak, double &dd, double &rj, double c)
 {
+#if MCTS_STEP_ORDER == 1
+    rj = rj + c;
+    E = E + c;
+#else
     E = E + c;
     rj = rj + c;
+#endif
     const double u = E - peak;
 #if defined(__CUDA_ARCH__)
     // peak before drawdown: the other order costs ptxas ~2 more register moves per step
+#if MCTS_STEP_ORDER == 2
+    if constexpr ((SEL & 2) != 0) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
+    if constexpr ((SEL & 1) != 0) psel_gt0<INT_SIGN>(peak, u, E);
+    else peak = (INT_SIGN ? gt_zero_hi(u) : (u > 0.0)) ? E : peak;
+#else
     if constexpr ((SEL & 1) != 0) psel_gt0<INT_SIGN>(peak, u, E);
     else peak = (INT_SIGN ? gt_zero_hi(u) : (u > 0.0)) ? E : peak;
     if constexpr ((SEL & 2) != 0) psel_lt(dd, u); else dd = (u < dd) ? u : dd;
+#endif
 #else
     peak = (u > 0.0) ? E : peak;
     dd = (u < dd) ? u : dd;
@@ -402,6 +421,26 @@ template <class IDS, bool BINARY, int SEL, class SRC, class SINK>
 MCTS_HD void eval_block8(Acc<IDS::N> &a, uint32_t W, SRC &src, SINK &sink, int t0)
 {
     const Masks m = BINARY ? make_masks_binary(W, a.h) : make_masks(W, W ^ 0x11111111u, a.h);
+#if MCTS_NEST == 1
+    if constexpr (std::is_same<SINK, NoSink>::value) {  // strategy-major source order (experiment)
+        double v1[8], v2[8], v3[8];
+        static_for<8>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            src.template get<i>(v1[i], v2[i], v3[i]);
+        });
+        static_for<IDS::N>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            constexpr int rule = rule_of_id(IDS::id(s));
+            static_for<8>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                const Preds p = trade_preds<BINARY>(m, mask_bit(i));
+                const double c = contribution<rule, SRC::kSharedLo>(p, v1[i], v2[i], v3[i]);
+                trade_step<(i < (SEL >> 2) ? 0 : (SEL & 3)), SRC::kIntSign>(a.E[s], a.peak[s], a.dd[s], a.r[s][i], c);
+            });
+        });
+        return;
+    }
+#endif
     static_for<8>([&](auto I) {
         constexpr int i = decltype(I)::value;
         double v1, v2, v3;

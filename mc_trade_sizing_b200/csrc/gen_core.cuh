@@ -9,11 +9,17 @@
 //       thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).
 //       Only the per-category COUNTS survive, because the reference shuffles every sequence before
 //       using it (:491-492) and a shuffled sequence is a uniform permutation of its multiset.
-//   path (sim, k), trade t (the np.random.shuffle of :492): the next trade is drawn from the urn of
-//       remaining counts, category = first r with idx < C_r, idx = mulhi32(x, remaining),
-//       x = word (t%4) of Philox(ctr = (t/4, k, sim, 1)).  Sequential urn draws generate a uniform
-//       permutation of the multiset, exactly the distribution Fisher-Yates gives; the multiply-shift
-//       index has bias <= remaining / 2^32 (< 2.4e-7 for 1000 trades).
+//   path (sim, k) (the np.random.shuffle of :492): a uniform permutation of the simulation's multiset, generated one of two ways
+//       by the number K of distinct values that can occur in the run:
+//       K <= 6   sequential draws from the URN of remaining counts (gen_path_codes_urn): the n-th draw of 8-trade block b takes the
+//                first value r with idx < C_r (C = cumulative remaining counts in value order), idx = mulhi32(x, remaining),
+//                x = word (n%4) of Philox(ctr = (2b + n/4, k, sim, 1)), and fills trade 8b + 7 - n (a partial last block of m trades:
+//                8b + m - 1 - n).  No array, no read-modify-write: K - 1 compares / predicated decrements per trade.
+//       K  > 6   Fisher-Yates over the packed code column in shared memory (gen_path_codes_fy), exactly the loop of
+//                RandomState.shuffle:  for i = L-1 .. 1:  j = mulhi32(x_i, i + 1);  swap(a_i, a_j),  x_i = word (i%4) of
+//                Philox(ctr = (i/4, k, sim, 1)).
+//       Both yield a uniform permutation of the multiset (sequential sampling without replacement, assigned to the positions in
+//       any fixed order, is exchangeable); the multiply-shift index has bias <= remaining / 2^32 (< 2.4e-7 for 1000 trades).
 #pragma once
 #include <stdint.h>
 
@@ -122,46 +128,52 @@ MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint
     }
 }
 
-// The urn of one path: cumulative remaining counts C_0 <= C_1 <= ... <= C_{K-1} = remaining.
+// The urn for a handful of values (K <= kMaxUrnValues): no array, no read-modify-write -- every draw is one multiply-high,
+// K - 1 compares against the cumulative remaining counts, K - 1 predicated decrements and a select chain for the code.  The n-th
+// draw of an 8-trade block fills trade 7 - n of the block (n = 0 .. 7; a partial last block of m trades fills m - 1 - n), which
+// lets the word be assembled as word * 16 + code; draw n uses word n % 4 of Philox(ctr = (2 * block + n / 4, k, sim, 1)).
+// Measured on the B200 against Fisher-Yates for the five values of the bench workload: k_sim_paths 19.72 -> 19.22 ms (six values:
+// 19.41 ms; from seven values on Fisher-Yates is cheaper).
+constexpr int kMaxUrnValues = 6;
+
+// The kernels are instantiated for urns of 2, 5 and 6 values; a run with 3 or 4 values uses the 5-value urn with empty categories
+// appended (an empty category at the end has the cumulative count `remaining` like the last real one, and the smallest matching
+// category wins).  0 = Fisher-Yates.
+MCTS_HD constexpr int urn_width(int K) { return K <= 2 ? 2 : K <= 5 ? 5 : K <= kMaxUrnValues ? 6 : 0; }
+
 template <int K>
-struct Urn {
-    uint32_t C[K > 1 ? K - 1 : 1];
-    uint32_t rem;
-    MCTS_HD void init(const uint32_t *counts)
-    {
-        uint32_t c = 0;
+MCTS_HD void gen_path_codes_urn(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t k, const uint32_t *counts, uint32_t *codes, int stride)
+{
+    static_assert(K >= 2 && K <= 8, "urn generator: 2 .. 8 values");
+    uint32_t C[K - 1], code[K];
+    uint32_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            c += counts[j];
-            if (j < K - 1) C[j] = c;
-        }
-        rem = c;
+    for (int j = 0; j < K; j++) {
+        code[j] = (g.rank_codes >> (4 * j)) & 15u;
+        acc += counts[j];
+        if (j < K - 1) C[j] = acc;
     }
-    // draw one trade; returns the category rank
-    MCTS_HD uint32_t draw(uint32_t x)
-    {
+    uint32_t rem = acc;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    auto draw = [&](uint32_t x) -> uint32_t {
         const uint32_t idx = mulhi32(x, rem);
-        uint32_t rank = 0;
+        uint32_t r = code[K - 1];
 #pragma unroll
-        for (int j = 0; j < K - 1; j++) {
-            const uint32_t lt = idx < C[j] ? 1u : 0u;
-            C[j] -= lt;
-            rank += 1u - lt;
+        for (int j = K - 2; j >= 0; j--) {  // the smallest category whose cumulative count exceeds idx
+#if defined(__CUDA_ARCH__)
+            // one compare, one PREDICATED in-place decrement, one select (written as C -= lt, ptxas emits an unconditional
+            // decrement into a new register plus a predicated move back: four instructions per category instead of three)
+            asm("{ .reg .pred p;\n\tsetp.lt.u32 p, %2, %0;\n\t@p add.u32 %0, %0, -1;\n\tselp.u32 %1, %3, %1, p; }"
+                : "+r"(C[j]), "+r"(r) : "r"(idx), "r"(code[j]));
+#else
+            const bool lt = idx < C[j];
+            r = lt ? code[j] : r;
+            C[j] -= lt ? 1u : 0u;
+#endif
         }
         rem -= 1u;
-        return rank;
-    }
-};
-
-// Generate the 4-bit outcome codes of path (sim, k): 8 trades per word, word `oct` stored at
-// codes[oct * stride].  The last word may be partial (upper nibbles 0).
-template <int K>
-MCTS_HD void gen_path_codes(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t k, const uint32_t *counts, uint32_t *codes, int stride)
-{
-    Urn<K> urn;
-    urn.init(counts);
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const uint32_t rank_codes = g.rank_codes;
+        return r;
+    };
     const int n_oct = g.L >> 3, tail = g.L & 7;
     for (int oct = 0; oct < n_oct; oct++) {
         uint32_t xa[4], xb[4];
@@ -169,10 +181,7 @@ MCTS_HD void gen_path_codes(const GenSpec &g, uint64_t seed, uint32_t sim, uint3
         philox4x32_10(k0, k1, 2u * oct + 1u, k, sim, kStreamShuffle, xb);
         uint32_t word = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t r = urn.draw(i < 4 ? xa[i] : xb[i - 4]);
-            word |= ((rank_codes >> (4u * r)) & 15u) << (4 * i);
-        }
+        for (int n = 0; n < 8; n++) word = word * 16u + draw(n < 4 ? xa[n] : xb[n - 4]);
         codes[(size_t)oct * stride] = word;
     }
     if (tail) {
@@ -181,12 +190,8 @@ MCTS_HD void gen_path_codes(const GenSpec &g, uint64_t seed, uint32_t sim, uint3
         philox4x32_10(k0, k1, 2u * n_oct + 1u, k, sim, kStreamShuffle, xb);
         uint32_t word = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (i < tail) {
-                const uint32_t r = urn.draw(i < 4 ? xa[i] : xb[i - 4]);
-                word |= ((rank_codes >> (4u * r)) & 15u) << (4 * i);
-            }
-        }
+        for (int n = 0; n < 8; n++)
+            if (n < tail) word = word * 16u + draw(n < 4 ? xa[n] : xb[n - 4]);
         codes[(size_t)n_oct * stride] = word;
     }
 }

@@ -180,9 +180,11 @@ __device__ __forceinline__ void generate_codes(const PathArgs &a, int64_t local,
     const int64_t sim = path / a.n_sh;
     const uint32_t k = (uint32_t)(path - sim * a.n_sh);
     const uint32_t *cnt = a.counts + (sim - a.sim0) * kMaxCat;
-    if constexpr (K == 2) {  // two distinct values: register urn
-        const uint32_t c2[2] = {__ldg(cnt), __ldg(cnt + 1)};
-        gen_path_codes<2>(a.g, a.seed, (uint32_t)sim, k, c2, column, stride);
+    if constexpr (K <= kMaxUrnValues) {  // a handful of values: the predicated urn, no array access at all (K = urn_width(g.K))
+        uint32_t c[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) c[j] = __ldg(cnt + j);   // counts beyond the run's own values are zero
+        gen_path_codes_urn<K>(a.g, a.seed, (uint32_t)sim, k, c, column, stride);
     } else {  // up to 16 values: Fisher-Yates on the packed column
         gen_path_codes_fy(a.g, a.seed, (uint32_t)sim, k, cnt, column, stride);
     }

@@ -777,8 +777,12 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
             k_sequences<KK, false><<<grid, kBlock, smem, h->stream>>>(a, h->d_values[0]);                                        \
         }                                                                                                                     \
     } while (0)
-    if (a.g.K <= 2) LAUNCH_SEQ(2);
-    else LAUNCH_SEQ(16);
+    switch (urn_width(a.g.K)) {  // the same generator the path kernels use for this run
+        case 2: LAUNCH_SEQ(2); break;
+        case 5: LAUNCH_SEQ(5); break;
+        case 6: LAUNCH_SEQ(6); break;
+        default: LAUNCH_SEQ(16); break;
+    }
 #undef LAUNCH_SEQ
     CUDA_TRY(cudaGetLastError());
     h->timing.launches++;

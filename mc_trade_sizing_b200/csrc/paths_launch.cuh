@@ -46,9 +46,14 @@ static cudaError_t launch_global(const PathArgs &a, cudaStream_t stream)
 template <int MODE>
 static cudaError_t launch_mode(const PathArgs &a, int block, cudaStream_t stream)
 {
-    if (block == 0) return a.g.K <= 2 ? launch_global<2, MODE>(a, stream) : launch_global<16, MODE>(a, stream);
-    if (a.g.K <= 2) return launch_k<2, MODE>(a, block, stream);  // two values: register urn
-    return launch_k<16, MODE>(a, block, stream);                // up to 16 values: Fisher-Yates in shared memory
+    const int uw = urn_width(a.g.K);  // 2 / 5 / 6: register urn of that many values; 0: Fisher-Yates on the code column
+    if (block == 0) return uw == 2 ? launch_global<2, MODE>(a, stream) : uw == 5 ? launch_global<5, MODE>(a, stream) : uw == 6 ? launch_global<6, MODE>(a, stream) : launch_global<16, MODE>(a, stream);
+    switch (uw) {
+        case 2: return launch_k<2, MODE>(a, block, stream);
+        case 5: return launch_k<5, MODE>(a, block, stream);
+        case 6: return launch_k<6, MODE>(a, block, stream);
+    }
+    return launch_k<16, MODE>(a, block, stream);
 }
 
 }  // namespace mcts
@@ -79,7 +84,11 @@ static cudaError_t launch_int_k(const PathArgs &a, int block, cudaStream_t strea
 template <int MODE>
 static cudaError_t launch_int_mode(const PathArgs &a, int block, cudaStream_t stream)
 {
-    if (a.g.K <= 2) return launch_int_k<2, MODE>(a, block, stream);
+    switch (urn_width(a.g.K)) {
+        case 2: return launch_int_k<2, MODE>(a, block, stream);
+        case 5: return launch_int_k<5, MODE>(a, block, stream);
+        case 6: return launch_int_k<6, MODE>(a, block, stream);
+    }
     return launch_int_k<16, MODE>(a, block, stream);
 }
 }  // namespace mcts

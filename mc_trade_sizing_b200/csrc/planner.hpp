@@ -71,9 +71,12 @@ struct SpecBuilder {
             status = MCTS_EINVAL;
             return false;
         }
-        s.cat_win = category(win);
-        s.cat_loss = category(-loss);
-        if (s.cat_win < 0 || s.cat_loss < 0 || g.n_seg >= kMaxSeg) {
+        // an outcome the acceptance test can never produce (p >= 1: no loss; p <= 0: no win) gets no category, so that it does not
+        // count towards K (which picks the generator and the urn width); its count is zero in every simulation anyway
+        const uint64_t kOne53 = (uint64_t)1 << 53;
+        s.cat_win = s.thr == 0 ? -1 : category(win);
+        s.cat_loss = s.thr >= kOne53 ? -1 : category(-loss);
+        if ((s.thr != 0 && s.cat_win < 0) || (s.thr < kOne53 && s.cat_loss < 0) || g.n_seg >= kMaxSeg) {
             status = MCTS_EUNSUPPORTED;
             err = "more than 32 distinct trade values in one run";
             return false;

@@ -12,13 +12,15 @@
  *     (2*(i%2), 2*(i%2)+1) of Philox(key = seed, ctr = (i/2, 0, sim, 0)) exactly like NumPy builds a
  *     double from two 32-bit words (a>>5, b>>6); the acceptance tests are the reference's own
  *     (`rand() < p`, choice(): `u < cdf[0]` after cdf normalisation) in floating point;
- *   - shuffle of path (sim, k) (np.random.shuffle of :492, Fisher-Yates from the top):
- *       the array starts as the distinct values in order of first appearance in the generator's
- *       value list, each repeated by its count;  for i = L-1 .. 1:  j = floor(x_i * (i+1) / 2^32),
- *       swap(a_i, a_j),  x_i = word (i%4) of Philox(ctr = (i/4, k, sim, 1));
- *     with exactly two distinct values the device uses sequential urn draws instead:
- *       for t = 0 .. L-1: the trade is the first value iff floor(x_t * remaining / 2^32) < remaining
- *       count of the first value.
+ *   - shuffle of path (sim, k) (np.random.shuffle of :492).  The run's VALUE LIST is the distinct values in order of first
+ *     appearance in the generator's (win, -loss) list, leaving out outcomes the acceptance test can never produce (a segment
+ *     whose normalised win probability is >= 1 has no loss value, one with <= 0 no win value).  With K values in the list:
+ *       K <= 6: sequential draws from the URN of remaining counts.  Trades are filled in blocks of 8: the n-th draw (n = 0..7)
+ *               of block b goes to trade 8b + 7 - n (a partial last block of m trades: 8b + m - 1 - n); it takes the first
+ *               value r of the list with idx < C_r, where C_r = remaining count of values 0..r and
+ *               idx = floor(x * remaining / 2^32), x = word (n%4) of Philox(ctr = (2b + n/4, k, sim, 1));
+ *       K  > 6: Fisher-Yates from the top: the array starts as the values in list order, each repeated by its count;
+ *               for i = L-1 .. 1:  j = floor(x_i * (i+1) / 2^32), swap(a_i, a_j),  x_i = word (i%4) of Philox(ctr = (i/4, k, sim, 1)).
  *
  * It shares the parameter struct of mcts_oracle.c and produces the post-shuffle sequences as doubles;
  * feeding them to oracle_eval_paths() gives the expected per-path results of mcts_simulate().
@@ -150,29 +152,36 @@ static int base_sequence(const dg_params *p, uint64_t seed, uint32_t sim, double
     return pos;
 }
 
-/* the distinct values of a run in order of first appearance in the generator's (win, -loss) list */
+/* normalised win probability of choice([w, -l], p=[p0, 1-p0]) as choice2() uses it */
+static double norm_p(double p0) { return p0 / (p0 + (1 - p0)); }
+
+/* the distinct values of a run in order of first appearance in the generator's (win, -loss) list; outcomes that the acceptance
+ * test `u < c0`, u in [0, 1), can never produce are left out (c0 >= 1: never a loss; c0 <= 0: never a win) */
 static int value_list(const dg_params *p, double *vals)
 {
     int n = p->num_trades, nv = 0;
     double cand[2 * DG_MAX_REGIMES + 8];
     int nc = 0;
+#define ADD_SEGMENT(w, l, p0)                   \
+    do {                                        \
+        double c0__ = norm_p(p0);               \
+        if (c0__ > 0.0) cand[nc++] = (w);       \
+        if (!(c0__ >= 1.0)) cand[nc++] = -(l);  \
+    } while (0)
     if (p->mode == 0) {
         int len[3] = {(int)(n * 0.2), (int)(n * 0.2), n - (int)(n * 0.4)};
+        double hr[3] = {fmin(p->hit_rate + 0.2, 1.0), fmax(p->hit_rate - 0.3, 0.05), p->hit_rate};
         double aw[3] = {p->avg_win * 1.1, p->avg_win * 0.9, p->avg_win};
         double al[3] = {p->avg_loss * 0.9, p->avg_loss * 1.1, p->avg_loss};
         int left = n;
         for (int k = 0; k < 3; k++) {
             int l = len[k] < left ? len[k] : left;
             if (l <= 0) continue;
-            cand[nc++] = aw[k];
-            cand[nc++] = -al[k];
+            ADD_SEGMENT(aw[k], al[k], hr[k]);
             left -= l;
             if (left <= 0) break;
         }
-        if (left > 0) {
-            cand[nc++] = p->avg_win;
-            cand[nc++] = -p->avg_loss;
-        }
+        if (left > 0) ADD_SEGMENT(p->avg_win, p->avg_loss, p->hit_rate);
     } else if (p->mode == 3) {
         dg_regime def[3] = {{(int)(n * 0.3), 0.9, 200, 100}, {(int)(n * 0.2), 0.5, 100, 100}, {n - (int)(n * 0.5), 0.2, 100, 200}};
         const dg_regime *rg = p->n_regimes < 0 ? def : p->regimes;
@@ -180,8 +189,7 @@ static int value_list(const dg_params *p, double *vals)
         for (int k = 0; k < nr; k++) {
             int l = rg[k].length < left ? rg[k].length : left;
             if (l <= 0) continue;
-            cand[nc++] = rg[k].avg_win;
-            cand[nc++] = -rg[k].avg_loss;
+            ADD_SEGMENT(rg[k].avg_win, rg[k].avg_loss, rg[k].hit_rate);
             left -= l;
             if (left <= 0) break;
         }
@@ -189,6 +197,7 @@ static int value_list(const dg_params *p, double *vals)
         cand[nc++] = p->avg_win;
         cand[nc++] = -p->avg_loss;
     }
+#undef ADD_SEGMENT
     for (int i = 0; i < nc; i++) {
         int seen = 0;
         for (int j = 0; j < nv; j++) seen |= memcmp(&vals[j], &cand[i], 8) == 0;
@@ -227,21 +236,31 @@ int64_t devgen_sequences(const dg_params *p, uint64_t seed, int64_t first_path, 
             for (int t = 0; t < c; t++) arr[pos++] = vals[v];
         }
         uint32_t x[4];
-        if (nv <= 2) { /* urn over two values */
-            uint32_t rem = (uint32_t)len, c0 = (uint32_t)first_count;
-            for (int t = 0; t < len; t++) {
-                if ((t & 3) == 0) {
-                    uint32_t ctr[4] = {(uint32_t)t >> 2, k, sim, 1u};
-                    philox((uint32_t)seed, (uint32_t)(seed >> 32), ctr, x);
+        (void)first_count;
+        if (nv <= 6) { /* urn over the value list */
+            uint32_t cnt[6] = {0, 0, 0, 0, 0, 0}, rem = (uint32_t)len;
+            for (int v = 0; v < nv; v++)
+                for (int t = 0; t < len; t++) cnt[v] += memcmp(&base[t], &vals[v], 8) == 0;
+            for (int b = 0; 8 * b < len; b++) {
+                int m = len - 8 * b < 8 ? len - 8 * b : 8;
+                for (int nd = 0; nd < m; nd++) {
+                    if ((nd & 3) == 0) {
+                        uint32_t ctr[4] = {2u * (uint32_t)b + (uint32_t)(nd >> 2), k, sim, 1u};
+                        philox((uint32_t)seed, (uint32_t)(seed >> 32), ctr, x);
+                    }
+                    uint32_t idx = (uint32_t)(((uint64_t)x[nd & 3] * rem) >> 32), cum = 0;
+                    int r = nv - 1;
+                    for (int v = 0; v < nv; v++) {
+                        cum += cnt[v];
+                        if (idx < cum) {
+                            r = v;
+                            break;
+                        }
+                    }
+                    cnt[r]--;
+                    rem--;
+                    out[q * len + 8 * b + m - 1 - nd] = vals[r];
                 }
-                uint32_t idx = (uint32_t)(((uint64_t)x[t & 3] * rem) >> 32);
-                if (idx < c0) {
-                    out[q * len + t] = vals[0];
-                    c0--;
-                } else {
-                    out[q * len + t] = vals[nv > 1 ? 1 : 0];
-                }
-                rem--;
             }
         } else { /* Fisher-Yates from the top */
             for (int i = len - 1; i >= 1; i--) {

@@ -112,8 +112,12 @@ int h_simulate(const mcts_params *p, uint64_t seed, int mode, double *profit, do
             }
             continue;
         }
-        if (g.K <= 2) gen_path_codes<2>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
-        else gen_path_codes_fy(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1);
+        switch (urn_width(g.K)) {  // the dispatch of paths_launch.cuh
+            case 2: gen_path_codes_urn<2>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1); break;
+            case 5: gen_path_codes_urn<5>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1); break;
+            case 6: gen_path_codes_urn<6>(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1); break;
+            default: gen_path_codes_fy(g, seed, (uint32_t)sim, k, cnt, codes.data(), 1); break;
+        }
         if (seqs)
             for (int t = 0; t < g.L; t++) seqs[i * g.L + t] = g.tab[(codes[t >> 3] >> (4 * (t & 7))) & 15].v1;
         if (profit && want_int && g.all_int) {

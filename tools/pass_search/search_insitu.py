@@ -38,6 +38,7 @@ ap.add_argument("--chains", type=int, default=7)
 ap.add_argument("--sel", type=int, default=7)
 ap.add_argument("--noinline", type=int, default=0)
 ap.add_argument("--start", default="")
+ap.add_argument("--extra", default="", help="extra #define lines for the candidate header, e.g. 'MCTS_NEST 1;MCTS_STEP_ORDER 1'")
 ap.add_argument("--kernel", default="full", choices=["full", "replay"], help="full: k_sim_paths (MCTS_FP*, MCTS_SEL_FULL); replay: k_replay_paths (MCTS_RP*, MCTS_SEL_REPLAY)")
 args = ap.parse_args()
 if args.start:
@@ -59,6 +60,7 @@ def score(tag, passes):
         prefix, selname = ("MCTS_FP", "MCTS_SEL_FULL") if args.kernel == "full" else ("MCTS_RP", "MCTS_SEL_REPLAY")
         f.write("".join("#define %s%d %s\n" % (prefix, j, ", ".join(map(str, p))) for j, p in enumerate(passes)))
         f.write("#define %s %d\n#define MCTS_NOINLINE_PASSES %d\n" % (selname, args.sel, args.noinline))
+        f.write("".join("#define %s\n" % d.strip() for d in args.extra.split(";") if d.strip()))
     cmd = ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-I", os.path.join(ROOT, "mc_trade_sizing_b200", "csrc"),
            "-include", hdr, "-cubin", "-o", cub, os.path.join(HERE, "one_%s.cu" % args.kernel)]
     if subprocess.run(cmd, capture_output=True).returncode:

@@ -66,13 +66,14 @@ struct IdList {
 // chain from a value read from constant memory (c_chain_start, -0.0 at run time) that the compiler cannot see
 // through: nothing is merged, all 20 state machines are carried to the end.  Which classes share a pass and
 // the order the ids are written in decides how well ptxas allocates the register pairs of the 8-trade loop
-// body: the lists below are the best of a search (tools/pass_search) scored by the SASS instruction count of
-// the loop bodies and confirmed on the B200.
+// body: the lists below come from a search (tools/pass_search) scored by the SASS instruction count of the loop
+// bodies, followed by timing the ~140 shortest candidates on the B200 (tools/autotune): the fastest measured
+// (19.17 ms per 2.1 M paths; SASS 1878 instructions per 8 trades x 20 ids, the shortest found is 1853 at 19.21 ms).
 #ifndef MCTS_FP0
-#define MCTS_FP0 9, 10, 6, 15, 7
-#define MCTS_FP1 14, 4, 5, 8, 17
-#define MCTS_FP2 3, 18, 1, 12, 11
-#define MCTS_FP3 2, 16, 19, 20, 13
+#define MCTS_FP0 4, 5, 14, 20, 17
+#define MCTS_FP1 9, 10, 7, 6, 15
+#define MCTS_FP2 13, 8, 16, 19, 2
+#define MCTS_FP3 3, 12, 1, 11, 18
 #endif
 // the replay kernel (caller-supplied values, kernels.cuh k_replay_paths) evaluates the same ids with a different value source;
 // its loop bodies are allocated differently by ptxas, so it has pass lists of its own from the same search

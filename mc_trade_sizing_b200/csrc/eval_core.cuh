@@ -83,6 +83,17 @@ struct IdList {
 #define MCTS_RP2 MCTS_FP2
 #define MCTS_RP3 MCTS_FP3
 #endif
+// curve export (HBM-bound, its sink keeps one more double per id): the lists that compile without spills there
+#ifndef MCTS_CP0
+#define MCTS_CP0 9, 10, 6, 15, 7
+#define MCTS_CP1 14, 4, 5, 8, 17
+#define MCTS_CP2 3, 18, 1, 12, 11
+#define MCTS_CP3 2, 16, 19, 20, 13
+#endif
+using CurvePass0 = IdList<MCTS_CP0>;
+using CurvePass1 = IdList<MCTS_CP1>;
+using CurvePass2 = IdList<MCTS_CP2>;
+using CurvePass3 = IdList<MCTS_CP3>;
 using ReplayPass0 = IdList<MCTS_RP0>;
 using ReplayPass1 = IdList<MCTS_RP1>;
 using ReplayPass2 = IdList<MCTS_RP2>;
@@ -129,6 +140,7 @@ constexpr bool full_passes_cover_all_ids()
     for (int id = 1; id <= 20; id++) {
         if (count_id<FullPass0>(id) + count_id<FullPass1>(id) + count_id<FullPass2>(id) + count_id<FullPass3>(id) != 1) return false;
         if (count_id<ReplayPass0>(id) + count_id<ReplayPass1>(id) + count_id<ReplayPass2>(id) + count_id<ReplayPass3>(id) != 1) return false;
+        if (count_id<CurvePass0>(id) + count_id<CurvePass1>(id) + count_id<CurvePass2>(id) + count_id<CurvePass3>(id) != 1) return false;
     }
     return true;
 }

@@ -228,6 +228,15 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths(cons
         if (active) run_pass_k<DedupPass1, MODE, sel_of_mode(MODE)>(src, a, local);
         __syncthreads();
         if (active) run_pass_k<DedupPass2, MODE, sel_of_mode(MODE)>(src, a, local);
+    } else if constexpr (MODE == PM_CURVES) {
+        __syncthreads();
+        if (active) run_pass_k<CurvePass0, MODE, sel_of_mode(MODE)>(src, a, local);
+        __syncthreads();
+        if (active) run_pass_k<CurvePass1, MODE, sel_of_mode(MODE)>(src, a, local);
+        __syncthreads();
+        if (active) run_pass_k<CurvePass2, MODE, sel_of_mode(MODE)>(src, a, local);
+        __syncthreads();
+        if (active) run_pass_k<CurvePass3, MODE, sel_of_mode(MODE)>(src, a, local);
     } else {
         __syncthreads();
         if (active) run_pass_k<FullPass0, MODE, sel_of_mode(MODE)>(src, a, local);

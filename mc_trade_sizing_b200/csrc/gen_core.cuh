@@ -4,9 +4,10 @@
 // src/trading_models.py:55,65,70,77,79,89,101,119,492) by Philox4x32-10 keyed with the user seed
 // and countered by (simulation, shuffle, trade), so any path can be regenerated anywhere:
 //
-//   base multiset of simulation `sim` (generators :43-128): uniform #i is the 53-bit integer built
-//       from words (2*(i%2), 2*(i%2)+1) of Philox(ctr = (i/2, 0, sim, 0)); win <=> integer < thr,
-//       thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).
+//   base multiset of simulation `sim` (generators :43-128): uniform #i is the 53-bit integer k_i = (a >> 5) * 2^26 + (b >> 6) with
+//       a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)) and b = word (i%4) of Philox(ctr = (i/4, 1, sim, 0)); win <=> k_i < thr,
+//       thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).  (The device computes b only when the
+//       top 27 bits tie with thr's.)
 //       Only the per-category COUNTS survive, because the reference shuffles every sequence before
 //       using it (:491-492) and a shuffled sequence is a uniform permutation of its multiset.
 //   path (sim, k) (the np.random.shuffle of :492): a uniform permutation of the simulation's multiset, generated one of two ways
@@ -72,12 +73,24 @@ struct BaseStream {
         sim = sim_;
         i = 0;
     }
-    MCTS_HD uint64_t next()
+    // Is the i-th 53-bit uniform integer k_i below thr (win <=> u < p, thr = ceil(p * 2^53))?  k_i = (a >> 5) * 2^26 + (b >> 6),
+    // a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)), b = word (i%4) of Philox(ctr = (i/4, 1, sim, 0)) -- NumPy's recipe for a
+    // double from two 32-bit words.  The top 27 bits decide unless they tie with thr's (probability 2^-27), so the second block
+    // is generated only then: four Bernoulli draws per Philox block instead of two, the same law.
+    MCTS_HD bool next_lt(uint64_t thr)
     {
-        if ((i & 1u) == 0u) philox4x32_10(k0, k1, i >> 1, 0u, sim, kStreamBase, x);
-        const uint32_t a = (i & 1u) ? x[2] : x[0], b = (i & 1u) ? x[3] : x[1];
+        if ((i & 3u) == 0u) philox4x32_10(k0, k1, i >> 2, 0u, sim, kStreamBase, x);
+        const uint32_t a = (i & 2u) ? ((i & 1u) ? x[3] : x[2]) : ((i & 1u) ? x[1] : x[0]);
+        const uint32_t hi = a >> 5, thr_hi = (uint32_t)(thr >> 26);
+        bool lt = hi < thr_hi;
+        if (hi == thr_hi) {
+            uint32_t y[4];
+            philox4x32_10(k0, k1, i >> 2, 1u, sim, kStreamBase, y);
+            const uint32_t b = (i & 2u) ? ((i & 1u) ? y[3] : y[2]) : ((i & 1u) ? y[1] : y[0]);
+            lt = (b >> 6) < (uint32_t)(thr & 0x3ffffffu);
+        }
         i++;
-        return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+        return lt;
     }
 };
 
@@ -92,7 +105,7 @@ MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint
         for (int s = 0; s < g.n_seg; s++) {
             const Segment sg = g.seg[s];
             uint32_t wins = 0;
-            for (int t = 0; t < sg.len; t++) wins += rs.next() < sg.thr ? 1u : 0u;
+            for (int t = 0; t < sg.len; t++) wins += rs.next_lt(sg.thr) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < kMaxCat; k++) {
                 counts[k] += (k == sg.cat_win ? wins : 0u) + (k == sg.cat_loss ? (uint32_t)sg.len - wins : 0u);
@@ -101,21 +114,21 @@ MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint
     } else {
         uint32_t wins = 0;
         if (g.kind == GEN_MARKOV1) {
-            uint32_t last = rs.next() < g.thr_init ? 1u : 0u;  // :70
+            uint32_t last = rs.next_lt(g.thr_init) ? 1u : 0u;  // :70
             wins = last;
             const uint64_t t_l = g.thr1[0], t_w = g.thr1[1];
             for (int t = 1; t < g.L; t++) {  // :74-84
-                last = rs.next() < (last ? t_w : t_l) ? 1u : 0u;
+                last = rs.next_lt(last ? t_w : t_l) ? 1u : 0u;
                 wins += last;
             }
         } else {
-            uint32_t older = rs.next() < g.thr_init ? 1u : 0u;  // :89, two unconditional trades
-            uint32_t newer = rs.next() < g.thr_init ? 1u : 0u;
+            uint32_t older = rs.next_lt(g.thr_init) ? 1u : 0u;  // :89, two unconditional trades
+            uint32_t newer = rs.next_lt(g.thr_init) ? 1u : 0u;
             wins = older + newer;
             const uint64_t t_ll = g.thr2[0], t_lw = g.thr2[1], t_wl = g.thr2[2], t_ww = g.thr2[3];
             for (int t = 2; t < g.L; t++) {  // :92-103
                 const uint64_t thr = older ? (newer ? t_ww : t_wl) : (newer ? t_lw : t_ll);
-                const uint32_t w = rs.next() < thr ? 1u : 0u;
+                const uint32_t w = rs.next_lt(thr) ? 1u : 0u;
                 wins += w;
                 older = newer;
                 newer = w;

@@ -9,7 +9,7 @@
  *   - base multiset of simulation `sim`: the reference generators of src/trading_models.py:43-128
  *     (three-phase dynamic incl. clipping and tail fill :44-65, Markov-1 :68-85, Markov-2 :87-104,
  *     regime switch :106-128) driven by uniforms u_i = k_i / 2^53, k_i built from words
- *     (2*(i%2), 2*(i%2)+1) of Philox(key = seed, ctr = (i/2, 0, sim, 0)) exactly like NumPy builds a
+ *     a = word (i%4) of Philox(key = seed, ctr = (i/4, 0, sim, 0)), b = the same word of ctr = (i/4, 1, sim, 0), combined exactly like NumPy builds a
  *     double from two 32-bit words (a>>5, b>>6); the acceptance tests are the reference's own
  *     (`rand() < p`, choice(): `u < cdf[0]` after cdf normalisation) in floating point;
  *   - shuffle of path (sim, k) (np.random.shuffle of :492).  The run's VALUE LIST is the distinct values in order of first
@@ -74,11 +74,12 @@ typedef struct {
 
 static double next_uniform(base_stream *s)
 {
-    if ((s->i & 1u) == 0u) {
-        uint32_t ctr[4] = {s->i >> 1, 0u, s->sim, 0u};
-        philox((uint32_t)s->seed, (uint32_t)(s->seed >> 32), ctr, s->buf);
-    }
-    uint32_t a = s->buf[(s->i & 1u) * 2u] >> 5, b = s->buf[(s->i & 1u) * 2u + 1u] >> 6;
+    /* u_i = ((a >> 5) * 2^26 + (b >> 6)) / 2^53, a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)), b = word (i%4) of
+     * Philox(ctr = (i/4, 1, sim, 0)) */
+    uint32_t ctr_a[4] = {s->i >> 2, 0u, s->sim, 0u}, ctr_b[4] = {s->i >> 2, 1u, s->sim, 0u}, xa[4], xb[4];
+    philox((uint32_t)s->seed, (uint32_t)(s->seed >> 32), ctr_a, xa);
+    philox((uint32_t)s->seed, (uint32_t)(s->seed >> 32), ctr_b, xb);
+    uint32_t a = xa[s->i & 3u] >> 5, b = xb[s->i & 3u] >> 6;
     s->i++;
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }

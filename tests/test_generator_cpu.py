@@ -177,3 +177,23 @@ def test_fuzz_generator_and_evaluator_against_the_oracles():
         assert_bitexact(out["dd"], exp["dd"], "%s %s dd" % (args, kw))
         ok += 1
     assert ok > 250 and err >= 5, (ok, err)
+
+
+def test_base_draw_tie_of_the_high_bits_uses_the_second_block():
+    """A Bernoulli draw of the base stream is decided by the top 27 bits of its 53-bit uniform unless they tie with the threshold's
+    (probability 2^-27); only then is the second Philox block generated.  Force the tie: pick the hit rate from the very word the
+    first draw will see, just above and just below the full 53-bit value, and check the outcome against the independent restatement."""
+    seed, sim = 987654321, 17
+    a = harness.philox((seed & 0xffffffff, seed >> 32), (0, 0, sim, 0))[0]
+    b = harness.philox((seed & 0xffffffff, seed >> 32), (0, 1, sim, 0))[0]
+    assert harness.philox((1, 2), (3, 4, 5, 6)) == oracle.devgen_philox((1, 2), (3, 4, 5, 6))
+    k = ((a >> 5) << 26) | (b >> 6)                       # the first uniform as a 53-bit integer
+    for thr, win in ((k + 1, 1), (k, 0), (k + 2 ** 20, 1), (max(k - 2 ** 20, (a >> 5) << 26), 0 if (b >> 6) >= 2 ** 20 else None)):
+        if win is None or thr >> 26 != a >> 5:
+            continue                                      # keep the high bits tied
+        p = thr / 2.0 ** 53                               # threshold53(p) == thr exactly (thr < 2^53 is representable)
+        prm = make_params(p, 186.0, 219.0, 1, 1, 1, use_markov=True)
+        counts, vals, L = harness.base_counts(prm, seed, sim)
+        assert L == 1 and int(counts[0]) == win, (thr, counts)
+        ref = oracle.devgen_sequences(oracle.make_params(p, 186.0, 219.0, 1, sim + 1, 1, use_markov=True), seed, first_path=sim, n=1)
+        assert (ref[0, 0] == 186.0) == bool(win)

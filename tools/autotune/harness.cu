@@ -13,6 +13,9 @@
 
 using namespace mcts;
 
+#ifndef HARNESS_BLOCK
+#define HARNESS_BLOCK 128   // threads per block (384 per SM in all)
+#endif
 #ifndef HARNESS_K
 #define HARNESS_K 16   // 16: Fisher-Yates generator; 5: five-value urn (the C5 parameters have five distinct values)
 #endif
@@ -64,8 +67,8 @@ int main(int argc, char **argv)
     a.sched = d_sched;
     a.out = d_out;
     a.ld = ld;
-    const size_t smem = (size_t)kTabWords * 4 + (size_t)((g.L + 7) / 8) * 128 * 4;
-    CK(cudaFuncSetAttribute(k_sim_paths<HARNESS_K, PM_FULL, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const size_t smem = (size_t)kTabWords * 4 + (size_t)((g.L + 7) / 8) * HARNESS_BLOCK * 4;
+    CK(cudaFuncSetAttribute(k_sim_paths<HARNESS_K, PM_FULL, HARNESS_BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -73,7 +76,7 @@ int main(int argc, char **argv)
     for (int rep = 0; rep < 5; rep++) {
         a.seed = seed + rep;
         CK(cudaEventRecord(e0));
-        k_sim_paths<HARNESS_K, PM_FULL, 128, false><<<(unsigned)((n + 127) / 128), 128, smem>>>(a);
+        k_sim_paths<HARNESS_K, PM_FULL, HARNESS_BLOCK, false><<<(unsigned)((n + HARNESS_BLOCK - 1) / HARNESS_BLOCK), HARNESS_BLOCK, smem>>>(a);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms;

@@ -47,6 +47,16 @@ def socket_path() -> str:
     return os.environ.get("MCTS_SERVER_SOCKET") or os.path.join(socket_dir(), "server.sock")
 
 
+def _private_dir(d: str) -> str:
+    """Create the socket directory (0700) or verify that an existing one belongs to this user and nobody else can write to it:
+    whoever can replace the socket could answer the CLI's requests."""
+    os.makedirs(d, mode=0o700, exist_ok=True)
+    st = os.stat(d)
+    if st.st_uid != os.getuid() or (st.st_mode & 0o022):
+        raise RuntimeError("mcts server directory %s is not private to uid %d (owner %d, mode %o)" % (d, os.getuid(), st.st_uid, st.st_mode & 0o777))
+    return d
+
+
 # ---- client -------------------------------------------------------------------------------------------------
 
 
@@ -63,8 +73,7 @@ def _connect(timeout=None):
 
 def _spawn_daemon():
     import subprocess
-    d = socket_dir()
-    os.makedirs(d, mode=0o700, exist_ok=True)
+    d = _private_dir(socket_dir())
     env = dict(os.environ)
     env.pop("MCTS_SERVER", None)  # the daemon itself computes
     env["PYTHONPATH"] = PKG_PARENT + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
@@ -81,8 +90,7 @@ def ensure_server(wait_s: float = 120.0):
     if s is not None:
         return s
     import fcntl
-    d = socket_dir()
-    os.makedirs(d, mode=0o700, exist_ok=True)
+    d = _private_dir(socket_dir())
     with open(os.path.join(d, "spawn.lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         s = _connect(timeout=wait_s)
@@ -187,7 +195,7 @@ def serve(idle_s: float = 120.0, engines: int = 3) -> int:
     from . import trading_models as tm
 
     path = socket_path()
-    os.makedirs(os.path.dirname(path), mode=0o700, exist_ok=True)
+    _private_dir(os.path.dirname(path))
     pool = _Pool(engines)
     stats = {"requests": 0, "runs": 0, "errors": 0, "started": time.time(), "busy": 0, "max_concurrent": 0, "last": time.time()}
     stats_lock = threading.Lock()

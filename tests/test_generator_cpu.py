@@ -1,6 +1,7 @@
 """CPU unit tests of the DEVICE generator code (csrc/gen_core.cuh via tests/cpu_harness): Philox
 known answers, base-sequence laws, urn shuffle, counter keying."""
 import numpy as np
+import pytest
 
 import harness
 from conftest import assert_bitexact
@@ -197,3 +198,39 @@ def test_base_draw_tie_of_the_high_bits_uses_the_second_block():
         assert L == 1 and int(counts[0]) == win, (thr, counts)
         ref = oracle.devgen_sequences(oracle.make_params(p, 186.0, 219.0, 1, sim + 1, 1, use_markov=True), seed, first_path=sim, n=1)
         assert (ref[0, 0] == 186.0) == bool(win)
+
+
+def _regime(length, hit, win, loss):
+    return {"length": length, "hit_rate": hit, "avg_win": win, "avg_loss": loss}
+
+
+URN_EDGE_CASES = [
+    ("K1_all_wins", (1.0, 10.0, 7.0, 37, 4, 3), dict(use_regime=True, regimes=[_regime(37, 1.0, 10.0, 7.0)])),               # one value: 2-urn, empty second category
+    ("K2_regime", (0.5, 1.0, 1.0, 50, 4, 3), dict(use_regime=True, regimes=[_regime(50, 0.4, 12.5, 3.25)])),
+    ("K3_p1_segment", (0.5, 1.0, 1.0, 64, 4, 3), dict(use_regime=True, regimes=[_regime(30, 1.0, 5.0, 9.0), _regime(34, 0.5, 6.5, 2.0)])),    # 5-urn padded
+    ("K4_two_regimes", (0.5, 1.0, 1.0, 70, 4, 3), dict(use_regime=True, regimes=[_regime(30, 0.7, 5.0, 9.0), _regime(40, 0.5, 6.5, 2.0)])),  # 5-urn padded
+    ("K5_default_dynamic", (0.82, 186.0, 219.0, 100, 4, 3), {}),                                                              # phase 1 has p = 1: five values
+    ("K6_dynamic", (0.6, 186.0, 219.0, 100, 4, 3), {}),                                                                       # 6-urn
+    ("K6_three_regimes", (0.5, 1.0, 1.0, 90, 4, 3), dict(use_regime=True, regimes=[_regime(30, 0.7, 5.0, 9.0), _regime(30, 0.5, 6.5, 2.0), _regime(30, 0.2, 1.5, 2.5)])),
+    ("K7_fisher_yates", (0.5, 1.0, 1.0, 120, 4, 3), dict(use_regime=True, regimes=[_regime(30, 0.7, 5.0, 9.0), _regime(30, 0.5, 6.5, 2.0), _regime(30, 0.2, 1.5, 2.5),
+                                                                                        _regime(30, 0.0, 8.0, 4.0)])),         # the 4th regime never wins: 7 values
+    ("K8_fisher_yates", (0.5, 1.0, 1.0, 121, 4, 3), dict(use_regime=True, regimes=[_regime(30, 0.7, 5.0, 9.0), _regime(30, 0.5, 6.5, 2.0), _regime(30, 0.2, 1.5, 2.5),
+                                                                                        _regime(31, 0.3, 8.0, 4.0)])),
+]
+
+
+@pytest.mark.parametrize("name,args,kw", URN_EDGE_CASES, ids=[c[0] for c in URN_EDGE_CASES])
+def test_generator_choice_at_the_value_count_boundaries(name, args, kw):
+    """Urn (<= 6 values that can occur, kernels instantiated for 2 / 5 / 6 with empty categories appended) vs Fisher-Yates (more), and
+    the rule that impossible outcomes (p >= 1: no loss, p <= 0: no win) get no category: the device code (g++ build) and the
+    independent restatement must produce the same sequences, each a permutation of its simulation's multiset."""
+    prm = make_params(*args, **kw)
+    out = harness.simulate(prm, 321, want_eval=True)
+    ref = oracle.devgen_sequences(oracle.make_params(*args, **kw), 321)
+    assert_bitexact(out["seqs"], ref, name + " sequences")
+    exp = oracle.eval_paths(ref, num_trades=args[3])
+    assert_bitexact(out["profit"], exp["profit"], name + " profit")
+    n_sh = args[5]
+    for sim in range(args[4]):
+        rows = np.sort(out["seqs"][sim * n_sh:(sim + 1) * n_sh], axis=1)
+        assert (rows == rows[0]).all(), name

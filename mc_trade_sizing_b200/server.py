@@ -221,7 +221,10 @@ def serve(idle_s: float = 120.0, engines: int = 3) -> int:
             try:
                 msg = json.loads(line.decode("utf-8"))
                 op = msg.get("op")
-                if op == "run":
+                if op == "run" and msg.get("protocol", PROTOCOL) != PROTOCOL:  # a daemon left over from another install
+                    rep = {"ok": False, "kind": "RuntimeError", "error": "protocol %r, this daemon speaks %d: stop it with "
+                           "`python -m mc_trade_sizing_b200.server --stop`" % (msg.get("protocol"), PROTOCOL)}
+                elif op == "run":
                     rep = {"ok": True, "rows": run(msg)}
                     with stats_lock:
                         stats["runs"] += 1

@@ -111,6 +111,12 @@ def test_errors_keep_their_type(daemon, monkeypatch):
     assert server.request({"op": "stats"}, start=False)["errors"] == 1
 
 
+def test_other_protocol_version_is_refused(daemon):
+    rep = server.request({"op": "run", "protocol": server.PROTOCOL + 1, "args": list(ARGS), "kwargs": {}, "seed": 1}, start=False)
+    assert rep["ok"] is False and rep["kind"] == "RuntimeError" and "protocol" in rep["error"]
+    assert server.request({"op": "stats"}, start=False)["runs"] == 0
+
+
 def test_cli_client_is_thin_and_prints_the_reference_table(daemon):
     """The CLI through the daemon: same stdout as a direct run, and the client process never loads NumPy or ctypes."""
     code = ("import sys; sys.argv = ['trading_models.py', '--hit_rate', '0.82', '--avg_win', '186', '--avg_loss', '219', '--num_simulations', '6',"

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -178,13 +180,29 @@ static int init_handle(mcts_handle *h)
     return MCTS_OK;
 }
 
+// No C++ exception may cross the C ABI (ctypes / cgo callers cannot unwind it): allocation failures of the host-side
+// containers and thread start-up failures become error codes like every other failure.
+template <class F>
+static int no_throw(F &&body) noexcept
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        try { return fail(MCTS_ENOMEM, "out of host memory"); } catch (...) { return MCTS_ENOMEM; }
+    } catch (const std::exception &e) {
+        try { return fail(MCTS_ECUDA, std::string("internal error: ") + e.what()); } catch (...) { return MCTS_ECUDA; }
+    } catch (...) {
+        return MCTS_ECUDA;
+    }
+}
+
 extern "C" {
 
 int mcts_abi_version(void) { return MCTS_ABI_VERSION; }
 
 const char *mcts_last_error(void) { return g_err.c_str(); }
 
-int mcts_create(int device, mcts_handle **out)
+static int mcts_create_impl(int device, mcts_handle **out)
 {
     if (!out) return fail(MCTS_EINVAL, "mcts_create: out is NULL");
     *out = nullptr;
@@ -266,7 +284,7 @@ int64_t mcts_plan_count(int64_t P, int64_t chunk_paths)
     return (int64_t)f.size();
 }
 
-int mcts_plan(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_paths)
+static int mcts_plan_impl(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_paths)
 {
     if (P <= 0) return fail(MCTS_EEMPTY, "no paths");
     std::vector<int64_t> f, c;
@@ -278,7 +296,7 @@ int mcts_plan(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_pa
     return MCTS_OK;
 }
 
-int mcts_combine(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks, mcts_agg *agg)
+static int mcts_combine_impl(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks, mcts_agg *agg)
 {
     if (P <= 0 || !chunks || !agg) return fail(MCTS_EINVAL, "mcts_combine: bad arguments");
     const int64_t chunk = clamp_chunk(chunk_paths);
@@ -636,7 +654,7 @@ int mcts_simulate_chunks(mcts_handle *h, const mcts_params *p, uint64_t seed, co
     return simulate_range(h, p, seed, opt, chunk_begin, chunk_end, out, nullptr, nullptr);
 }
 
-int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+static int mcts_simulate_impl(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
 {
     if (!h || !p || !agg) return fail(MCTS_EINVAL, "NULL argument");
     const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
@@ -649,7 +667,7 @@ int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mct
     return mcts_combine(P, chunk, recs.data(), nc, agg);
 }
 
-int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+static int mcts_replay_impl(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
 {
     if (!h || !values || !agg) return fail(MCTS_EINVAL, "NULL argument");
     if (P <= 0 || T <= 0) return fail(MCTS_EEMPTY, "zero paths or an empty trade sequence");
@@ -738,7 +756,7 @@ static int path_range_args(mcts_handle *h, const mcts_params *p, uint64_t seed, 
     return MCTS_OK;
 }
 
-int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *values)
+static int mcts_sequences_impl(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *values)
 {
     if (!h || !p || !values) return fail(MCTS_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -793,7 +811,7 @@ int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t 
     return timing_collect(h);
 }
 
-int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *curves_dev)
+static int mcts_export_curves_impl(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *curves_dev)
 {
     if (!h || !p || !curves_dev) return fail(MCTS_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -956,7 +974,7 @@ int64_t mcts_auto_chunk(int64_t P, int n_shards)
     return clamp_chunk(std::min<int64_t>(c, (int64_t)1 << 22));
 }
 
-int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *bounds)
+static int mcts_plan_shards_impl(int64_t P, int64_t chunk_paths, int n_shards, int64_t *bounds)
 {
     if (P <= 0) return fail(MCTS_EEMPTY, "no paths");
     if (n_shards <= 0 || !bounds) return fail(MCTS_EINVAL, "mcts_plan_shards: bad arguments");
@@ -974,7 +992,7 @@ int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *boun
     return MCTS_OK;
 }
 
-int mcts_group_create(const int *devices, int n, mcts_group **out)
+static int mcts_group_create_impl(const int *devices, int n, mcts_group **out)
 {
     if (!out) return fail(MCTS_EINVAL, "mcts_group_create: out is NULL");
     *out = nullptr;
@@ -1028,7 +1046,7 @@ int mcts_group_get_timing(const mcts_group *g, mcts_timing *out)
     return MCTS_OK;
 }
 
-int mcts_group_simulate(mcts_group *g, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+static int mcts_group_simulate_impl(mcts_group *g, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
 {
     if (!g || g->dev.empty() || !p || !agg) return fail(MCTS_EINVAL, "NULL argument");
     const int64_t P = (int64_t)p->num_simulations * p->num_mc_shuffles;
@@ -1074,6 +1092,58 @@ int mcts_group_simulate(mcts_group *g, const mcts_params *p, uint64_t seed, cons
             return fail(rcs[d], buf + msgs[d]);
         }
     return mcts_combine(P, o.chunk_paths, recs.data(), nc, agg);
+}
+
+// ---- the exported entry points of everything above that allocates on the host ---------------------
+
+int mcts_create(int device, mcts_handle **out)
+{
+    return no_throw([&] { return mcts_create_impl(device, out); });
+}
+
+int mcts_plan(int64_t P, int64_t chunk_paths, int64_t *first_path, int64_t *n_paths)
+{
+    return no_throw([&] { return mcts_plan_impl(P, chunk_paths, first_path, n_paths); });
+}
+
+int mcts_combine(int64_t P, int64_t chunk_paths, const mcts_chunk_result *chunks, int64_t n_chunks, mcts_agg *agg)
+{
+    return no_throw([&] { return mcts_combine_impl(P, chunk_paths, chunks, n_chunks, agg); });
+}
+
+int mcts_simulate(mcts_handle *h, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    return no_throw([&] { return mcts_simulate_impl(h, p, seed, opt, agg, profit, dd); });
+}
+
+int mcts_replay(mcts_handle *h, const double *values, int64_t P, int64_t T, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    return no_throw([&] { return mcts_replay_impl(h, values, P, T, opt, agg, profit, dd); });
+}
+
+int mcts_sequences(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *values)
+{
+    return no_throw([&] { return mcts_sequences_impl(h, p, seed, first_path, n, values); });
+}
+
+int mcts_export_curves(mcts_handle *h, const mcts_params *p, uint64_t seed, int64_t first_path, int64_t n, double *curves_dev)
+{
+    return no_throw([&] { return mcts_export_curves_impl(h, p, seed, first_path, n, curves_dev); });
+}
+
+int mcts_plan_shards(int64_t P, int64_t chunk_paths, int n_shards, int64_t *bounds)
+{
+    return no_throw([&] { return mcts_plan_shards_impl(P, chunk_paths, n_shards, bounds); });
+}
+
+int mcts_group_create(const int *devices, int n, mcts_group **out)
+{
+    return no_throw([&] { return mcts_group_create_impl(devices, n, out); });
+}
+
+int mcts_group_simulate(mcts_group *g, const mcts_params *p, uint64_t seed, const mcts_options *opt, mcts_agg *agg, double *profit, double *dd)
+{
+    return no_throw([&] { return mcts_group_simulate_impl(g, p, seed, opt, agg, profit, dd); });
 }
 
 }  // extern "C"

@@ -308,10 +308,20 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(
 //   * two tiles: the copy of tile k+1 is in flight while tile k is evaluated (one barrier per tile);
 //   * all passes of a mode run inside ONE launch (they re-stream the block's rows, which the previous pass left in L2
 //     when the chunk is small enough), so a chunk is one launch instead of four.
+#ifndef MCTS_REPLAY_WARP_TILES
+#define MCTS_REPLAY_WARP_TILES 1
+#endif
 constexpr int kReplayBlock = 128;
 constexpr int kReplayTile = 32;                    // trades per tile = four 8-trade blocks
-constexpr int kReplayPitch = kReplayBlock + 1;     // doubles per tile row: odd -> conflict-free transposing writes
-constexpr size_t kReplaySmem = 2 * (size_t)kReplayTile * kReplayPitch * sizeof(double);   // 66 KB per block, 3 blocks per SM
+#if MCTS_REPLAY_WARP_TILES
+// every warp owns the tiles of its own 32 paths: no block barrier anywhere, the four warps of a block drift apart and
+// hide each other's copy latency
+constexpr int kReplayRows = 32;
+#else
+constexpr int kReplayRows = kReplayBlock;          // block-wide tiles, one __syncthreads per tile
+#endif
+constexpr int kReplayPitch = kReplayRows + 1;      // doubles per tile row: odd -> conflict-free transposing writes
+constexpr size_t kReplaySmem = (kReplayBlock / kReplayRows) * 2 * (size_t)kReplayTile * kReplayPitch * sizeof(double);   // 66 KB per block, 3 blocks per SM
 
 struct TileSource {
     static constexpr bool kSharedLo = false;  // arbitrary caller values
@@ -328,11 +338,15 @@ struct TileSource {
     __device__ __forceinline__ void issue(int tile)
     {
         if (tile < n_tiles) {
-            const int lane = copy_tid & 31, warp = copy_tid >> 5;
+            const int lane = copy_tid & 31;
             const int64_t t = (int64_t)tile * kReplayTile + lane;
             double *dst = tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)lane * kReplayPitch;
             if (t < T) {
-                for (int r = warp; r < n_rows; r += kReplayBlock / 32) {
+#if MCTS_REPLAY_WARP_TILES
+                for (int r = 0; r < n_rows; r++) {   // `rows`, `tiles` and `n_rows` are this WARP's
+#else
+                for (int r = copy_tid >> 5; r < n_rows; r += kReplayBlock / 32) {
+#endif
                     const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + r);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(rows + (int64_t)r * T + t) : "memory");
                 }
@@ -340,17 +354,25 @@ struct TileSource {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    __device__ __forceinline__ void sync_owners()
+    {
+#if MCTS_REPLAY_WARP_TILES
+        __syncwarp();
+#else
+        __syncthreads();
+#endif
+    }
     // start of a pass: nobody may still be reading the tiles of the previous pass
     __device__ __forceinline__ void begin_pass()
     {
-        __syncthreads();
+        sync_owners();
         issue(0);
     }
     // make tile `tile` readable and start the copy of the next one into the other buffer
     __device__ __forceinline__ void acquire(int tile)
     {
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of `tile` has landed ...
-        __syncthreads();                                      // ... and everybody's; everybody is done with tile - 1
+        sync_owners();                                        // ... and every owner's; every owner is done with tile - 1
         issue(tile + 1);
     }
     __device__ __forceinline__ const double *slot(int oct) const
@@ -402,23 +424,26 @@ struct TileSource {
     }
 };
 
-// Every thread of a block runs every pass (the tile barriers need all of them): threads beyond the last path of the launch
-// evaluate the block's last valid row again and store nothing.
+// Every thread of a tile's owner group (the warp, or the block with MCTS_REPLAY_WARP_TILES 0) runs every pass -- the copy is
+// cooperative: threads beyond the last path of the launch evaluate the group's last valid row again and store nothing; a
+// warp without any valid row leaves at once.
 template <int MODE>
 __global__ void __launch_bounds__(kReplayBlock, 3) k_replay_paths(const __grid_constant__ PathArgs a, const double *__restrict__ values, int64_t T)
 {
     extern __shared__ __align__(16) double replay_tiles[];
-    const int64_t first = (int64_t)blockIdx.x * kReplayBlock;
+    const int group = (int)threadIdx.x / kReplayRows, member = (int)threadIdx.x % kReplayRows;
+    const int64_t first = (int64_t)blockIdx.x * kReplayBlock + (int64_t)group * kReplayRows;
     const int64_t left = a.n - first;
+    if (left <= 0) return;  // whole owner group beyond the launch (never the case for block-wide tiles)
     TileSource src;
     src.rows = values + first * T;  // `values` already points at this launch's first path
     src.T = T;
-    src.n_rows = (int)(left < kReplayBlock ? left : kReplayBlock);
+    src.n_rows = (int)(left < kReplayRows ? left : kReplayRows);
     src.n_tiles = (int)((T + kReplayTile - 1) / kReplayTile);
-    src.tiles = replay_tiles;
-    src.tid = (int)threadIdx.x < src.n_rows ? (int)threadIdx.x : src.n_rows - 1;
-    src.copy_tid = (int)threadIdx.x;
-    const bool active = (int)threadIdx.x < src.n_rows;
+    src.tiles = replay_tiles + (size_t)group * 2 * kReplayTile * kReplayPitch;
+    src.tid = member < src.n_rows ? member : src.n_rows - 1;
+    src.copy_tid = member;
+    const bool active = member < src.n_rows;
     const int64_t local = first + src.tid;
     auto pass = [&](auto IDS) {
         using L = decltype(IDS);

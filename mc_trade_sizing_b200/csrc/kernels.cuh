@@ -311,8 +311,16 @@ __global__ void __launch_bounds__(BLOCK, kThreadsPerSM / BLOCK) k_sim_paths_int(
 #ifndef MCTS_REPLAY_WARP_TILES
 #define MCTS_REPLAY_WARP_TILES 1
 #endif
+#ifndef MCTS_REPLAY_TILE
+#define MCTS_REPLAY_TILE 32
+#endif
+#ifndef MCTS_REPLAY_STAGES
+#define MCTS_REPLAY_STAGES 2
+#endif
 constexpr int kReplayBlock = 128;
-constexpr int kReplayTile = 32;                    // trades per tile = four 8-trade blocks
+constexpr int kReplayTile = MCTS_REPLAY_TILE;      // trades per tile: 8, 16 or 32 (one lane copies one trade of one row)
+constexpr int kReplayStages = MCTS_REPLAY_STAGES;  // tiles per owner group: stages - 1 copies are in flight while one is evaluated
+static_assert((kReplayTile == 8 || kReplayTile == 16 || kReplayTile == 32) && kReplayStages >= 2 && kReplayStages <= 8, "replay tile geometry");
 #if MCTS_REPLAY_WARP_TILES
 // every warp owns the tiles of its own 32 paths: no block barrier anywhere, the four warps of a block drift apart and
 // hide each other's copy latency
@@ -321,7 +329,7 @@ constexpr int kReplayRows = 32;
 constexpr int kReplayRows = kReplayBlock;          // block-wide tiles, one __syncthreads per tile
 #endif
 constexpr int kReplayPitch = kReplayRows + 1;      // doubles per tile row: odd -> conflict-free transposing writes
-constexpr size_t kReplaySmem = (kReplayBlock / kReplayRows) * 2 * (size_t)kReplayTile * kReplayPitch * sizeof(double);   // 66 KB per block, 3 blocks per SM
+constexpr size_t kReplaySmem = (kReplayBlock / kReplayRows) * kReplayStages * (size_t)kReplayTile * kReplayPitch * sizeof(double);   // 66 KB per block, 3 blocks per SM
 
 struct TileSource {
     static constexpr bool kSharedLo = false;  // arbitrary caller values
@@ -330,7 +338,7 @@ struct TileSource {
     int64_t T;
     int n_rows;           // valid rows of this block (<= kReplayBlock)
     int n_tiles;
-    double *tiles;        // [2][kReplayTile][kReplayPitch] in shared memory
+    double *tiles;        // [kReplayStages][kReplayTile][kReplayPitch] in shared memory
     int tid;              // the row this thread EVALUATES (clamped to the last valid row of the block)
     int copy_tid;         // threadIdx.x: this thread's place in the cooperative copy
     double v[8];
@@ -338,14 +346,16 @@ struct TileSource {
     __device__ __forceinline__ void issue(int tile)
     {
         if (tile < n_tiles) {
-            const int lane = copy_tid & 31;
-            const int64_t t = (int64_t)tile * kReplayTile + lane;
-            double *dst = tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)lane * kReplayPitch;
+            // one copy instruction of a warp moves 32 / kReplayTile row segments of kReplayTile consecutive trades each
+            constexpr int kRowsPerCopy = 32 / kReplayTile;
+            const int lane = copy_tid & 31, tl = lane % kReplayTile, sub = lane / kReplayTile;
+            const int64_t t = (int64_t)tile * kReplayTile + tl;
+            double *dst = tiles + (size_t)(tile % kReplayStages) * kReplayTile * kReplayPitch + (size_t)tl * kReplayPitch;
             if (t < T) {
 #if MCTS_REPLAY_WARP_TILES
-                for (int r = 0; r < n_rows; r++) {   // `rows`, `tiles` and `n_rows` are this WARP's
+                for (int r = sub; r < n_rows; r += kRowsPerCopy) {   // `rows`, `tiles` and `n_rows` are this WARP's
 #else
-                for (int r = copy_tid >> 5; r < n_rows; r += kReplayBlock / 32) {
+                for (int r = (copy_tid >> 5) * kRowsPerCopy + sub; r < n_rows; r += (kReplayBlock / 32) * kRowsPerCopy) {
 #endif
                     const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + r);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(rows + (int64_t)r * T + t) : "memory");
@@ -366,19 +376,20 @@ struct TileSource {
     __device__ __forceinline__ void begin_pass()
     {
         sync_owners();
-        issue(0);
+#pragma unroll
+        for (int k = 0; k < kReplayStages - 1; k++) issue(k);
     }
     // make tile `tile` readable and start the copy of the next one into the other buffer
     __device__ __forceinline__ void acquire(int tile)
     {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of `tile` has landed ...
+        asm volatile("cp.async.wait_group %0;" ::"n"(kReplayStages - 2) : "memory");  // this thread's share of `tile` has landed ...
         sync_owners();                                        // ... and every owner's; every owner is done with tile - 1
-        issue(tile + 1);
+        issue(tile + kReplayStages - 1);
     }
     __device__ __forceinline__ const double *slot(int oct) const
     {
         const int tile = oct / (kReplayTile / 8), o = oct % (kReplayTile / 8);
-        return tiles + (size_t)(tile & 1) * kReplayTile * kReplayPitch + (size_t)(o * 8) * kReplayPitch + tid;
+        return tiles + (size_t)(tile % kReplayStages) * kReplayTile * kReplayPitch + (size_t)(o * 8) * kReplayPitch + tid;
     }
     __device__ __forceinline__ uint32_t load(int oct)
     {
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(kReplayBlock, 3) k_replay_paths(const __grid_c
     src.T = T;
     src.n_rows = (int)(left < kReplayRows ? left : kReplayRows);
     src.n_tiles = (int)((T + kReplayTile - 1) / kReplayTile);
-    src.tiles = replay_tiles + (size_t)group * 2 * kReplayTile * kReplayPitch;
+    src.tiles = replay_tiles + (size_t)group * kReplayStages * kReplayTile * kReplayPitch;
     src.tid = member < src.n_rows ? member : src.n_rows - 1;
     src.copy_tid = member;
     const bool active = member < src.n_rows;

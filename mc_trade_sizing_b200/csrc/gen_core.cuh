@@ -4,10 +4,10 @@
 // src/trading_models.py:55,65,70,77,79,89,101,119,492) by Philox4x32-10 keyed with the user seed
 // and countered by (simulation, shuffle, trade), so any path can be regenerated anywhere:
 //
-//   base multiset of simulation `sim` (generators :43-128): uniform #i is the 53-bit integer k_i = (a >> 5) * 2^26 + (b >> 6) with
-//       a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)) and b = word (i%4) of Philox(ctr = (i/4, 1, sim, 0)); win <=> k_i < thr,
-//       thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).  (The device computes b only when the
-//       top 27 bits tie with thr's.)
+//   base multiset of simulation `sim` (generators :43-128): uniform #i is the 53-bit integer k_i = h_i * 2^37 + rest_i with
+//       h_i = 16-bit half (i%8) of Philox(ctr = (i/8, 0, sim, 0)) and rest_i = the top 37 bits of y0:y1, y = Philox(ctr = (i, 1, sim, 0));
+//       win <=> k_i < thr, thr = ceil(p * 2^53) -- the same law as `np.random.rand() < p` / choice(p=[p, 1-p]).  (The device
+//       computes rest_i only when h_i ties with the top 16 bits of thr.)
 //       Only the per-category COUNTS survive, because the reference shuffles every sequence before
 //       using it (:491-492) and a shuffled sequence is a uniform permutation of its multiset.
 //   path (sim, k) (the np.random.shuffle of :492): a uniform permutation of the simulation's multiset, generated one of two ways
@@ -61,7 +61,15 @@ MCTS_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, u
 
 constexpr uint32_t kStreamBase = 0u, kStreamShuffle = 1u;
 
-// sequential reader of the 53-bit uniforms of one simulation's base stream
+// Sequential reader of the 53-bit uniforms of one simulation's base stream.
+//
+// Is the i-th 53-bit uniform integer k_i below thr (win <=> u < p, thr = ceil(p * 2^53))?
+//     k_i = h_i * 2^37 + rest_i
+//     h_i    = 16-bit half (i % 8) of Philox(ctr = (i / 8, 0, sim, 0)): word (i % 8) / 2, its upper half when i is even, lower when odd
+//     rest_i = the top 37 bits of the 64-bit number y0:y1, y = Philox(ctr = (i, 1, sim, 0))
+// The 16 bits of h_i decide unless they tie with thr's top 16 bits (probability 2^-16), so the second block is generated only
+// then: EIGHT Bernoulli draws per Philox block (round 1: two, round 2 first version: four), the same law -- k_i is uniform on
+// [0, 2^53) whatever part of it is looked at first.
 struct BaseStream {
     uint32_t k0, k1, sim;
     uint32_t i;
@@ -73,28 +81,57 @@ struct BaseStream {
         sim = sim_;
         i = 0;
     }
-    // Is the i-th 53-bit uniform integer k_i below thr (win <=> u < p, thr = ceil(p * 2^53))?  k_i = (a >> 5) * 2^26 + (b >> 6),
-    // a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)), b = word (i%4) of Philox(ctr = (i/4, 1, sim, 0)) -- NumPy's recipe for a
-    // double from two 32-bit words.  The top 27 bits decide unless they tie with thr's (probability 2^-27), so the second block
-    // is generated only then: four Bernoulli draws per Philox block instead of two, the same law.
+    MCTS_HD void load_block() { philox4x32_10(k0, k1, i >> 3, 0u, sim, kStreamBase, x); }
+    // the rare second look: draw `idx` tied with the top 16 bits of thr
+    MCTS_HD bool tie_break(uint32_t idx, uint64_t thr) const
+    {
+        uint32_t y[4];
+        philox4x32_10(k0, k1, idx, 1u, sim, kStreamBase, y);
+        const uint64_t rest = (((uint64_t)y[0] << 32) | (uint64_t)y[1]) >> 27;
+        return rest < (thr & ((1ull << 37) - 1ull));
+    }
+    // draw (i - i % 8) + J of the block in x, J a compile-time index; thr_hi = thr() >> 37 (thr() is evaluated on a tie only)
+    template <int J, class THR>
+    MCTS_HD bool lt_at(uint32_t thr_hi, THR &&thr) const
+    {
+        const uint32_t h = (J & 1) ? (x[J >> 1] & 0xffffu) : (x[J >> 1] >> 16);
+        bool lt = h < thr_hi;
+        if (h == thr_hi) lt = tie_break((i & ~7u) + (uint32_t)J, thr());
+        return lt;
+    }
     MCTS_HD bool next_lt(uint64_t thr)
     {
-        if ((i & 3u) == 0u) philox4x32_10(k0, k1, i >> 2, 0u, sim, kStreamBase, x);
-        const uint32_t a = (i & 2u) ? ((i & 1u) ? x[3] : x[2]) : ((i & 1u) ? x[1] : x[0]);
-        const uint32_t hi = a >> 5, thr_hi = (uint32_t)(thr >> 26);
-        bool lt = hi < thr_hi;
-        if (hi == thr_hi) {
-            uint32_t y[4];
-            philox4x32_10(k0, k1, i >> 2, 1u, sim, kStreamBase, y);
-            const uint32_t b = (i & 2u) ? ((i & 1u) ? y[3] : y[2]) : ((i & 1u) ? y[1] : y[0]);
-            lt = (b >> 6) < (uint32_t)(thr & 0x3ffffffu);
-        }
+        if ((i & 7u) == 0u) load_block();
+        const uint32_t w = (i & 4u) ? ((i & 2u) ? x[3] : x[2]) : ((i & 2u) ? x[1] : x[0]);
+        const uint32_t h = (i & 1u) ? (w & 0xffffu) : (w >> 16);
+        const uint32_t thr_hi = (uint32_t)(thr >> 37);
+        bool lt = h < thr_hi;
+        if (h == thr_hi) lt = tie_break(i, thr);
         i++;
         return lt;
     }
+    // the next eight draws against one threshold (i % 8 == 0): how many are below it
+    MCTS_HD uint32_t count_lt8(uint64_t thr)
+    {
+        load_block();
+        const uint32_t thr_hi = (uint32_t)(thr >> 37);
+        uint32_t wins = 0;
+        wins += lt_at<0>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<1>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<2>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<3>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<4>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<5>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<6>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        wins += lt_at<7>(thr_hi, [&] { return thr; }) ? 1u : 0u;
+        i += 8;
+        return wins;
+    }
 };
 
-// Per-category counts of the base sequence of one simulation (what :477-490 would have produced).
+// Per-category counts of the base sequence of one simulation (what :477-490 would have produced).  Whole Philox blocks of
+// eight draws take the unrolled forms (no word selection by index); the draws before the first block boundary and after
+// the last one go through next_lt.
 MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint32_t (&counts)[kMaxCat])
 {
 #pragma unroll
@@ -105,7 +142,10 @@ MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint
         for (int s = 0; s < g.n_seg; s++) {
             const Segment sg = g.seg[s];
             uint32_t wins = 0;
-            for (int t = 0; t < sg.len; t++) wins += rs.next_lt(sg.thr) ? 1u : 0u;
+            int t = 0;
+            for (; t < sg.len && (rs.i & 7u) != 0u; t++) wins += rs.next_lt(sg.thr) ? 1u : 0u;
+            for (; t + 8 <= sg.len; t += 8) wins += rs.count_lt8(sg.thr);
+            for (; t < sg.len; t++) wins += rs.next_lt(sg.thr) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < kMaxCat; k++) {
                 counts[k] += (k == sg.cat_win ? wins : 0u) + (k == sg.cat_loss ? (uint32_t)sg.len - wins : 0u);
@@ -117,22 +157,55 @@ MCTS_HD void gen_base_counts(const GenSpec &g, uint64_t seed, uint32_t sim, uint
             uint32_t last = rs.next_lt(g.thr_init) ? 1u : 0u;  // :70
             wins = last;
             const uint64_t t_l = g.thr1[0], t_w = g.thr1[1];
-            for (int t = 1; t < g.L; t++) {  // :74-84
-                last = rs.next_lt(last ? t_w : t_l) ? 1u : 0u;
+            const uint32_t h_l = (uint32_t)(t_l >> 37), h_w = (uint32_t)(t_w >> 37);
+            auto step = [&](bool lt) {
+                last = lt ? 1u : 0u;
                 wins += last;
+            };
+            int t = 1;
+            for (; t < g.L && (rs.i & 7u) != 0u; t++) step(rs.next_lt(last ? t_w : t_l));  // :74-84
+            for (; t + 8 <= g.L; t += 8) {
+                rs.load_block();
+                step(rs.lt_at<0>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<1>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<2>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<3>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<4>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<5>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<6>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                step(rs.lt_at<7>(last ? h_w : h_l, [&] { return last ? t_w : t_l; }));
+                rs.i += 8;
             }
+            for (; t < g.L; t++) step(rs.next_lt(last ? t_w : t_l));
         } else {
             uint32_t older = rs.next_lt(g.thr_init) ? 1u : 0u;  // :89, two unconditional trades
             uint32_t newer = rs.next_lt(g.thr_init) ? 1u : 0u;
             wins = older + newer;
             const uint64_t t_ll = g.thr2[0], t_lw = g.thr2[1], t_wl = g.thr2[2], t_ww = g.thr2[3];
-            for (int t = 2; t < g.L; t++) {  // :92-103
-                const uint64_t thr = older ? (newer ? t_ww : t_wl) : (newer ? t_lw : t_ll);
-                const uint32_t w = rs.next_lt(thr) ? 1u : 0u;
+            const uint32_t h_ll = (uint32_t)(t_ll >> 37), h_lw = (uint32_t)(t_lw >> 37), h_wl = (uint32_t)(t_wl >> 37), h_ww = (uint32_t)(t_ww >> 37);
+            auto thr_of = [&]() { return older ? (newer ? t_ww : t_wl) : (newer ? t_lw : t_ll); };
+            auto hi_of = [&]() { return older ? (newer ? h_ww : h_wl) : (newer ? h_lw : h_ll); };
+            auto step = [&](bool lt) {
+                const uint32_t w = lt ? 1u : 0u;
                 wins += w;
                 older = newer;
                 newer = w;
+            };
+            int t = 2;
+            for (; t < g.L && (rs.i & 7u) != 0u; t++) step(rs.next_lt(thr_of()));  // :92-103
+            for (; t + 8 <= g.L; t += 8) {
+                rs.load_block();
+                step(rs.lt_at<0>(hi_of(), thr_of));
+                step(rs.lt_at<1>(hi_of(), thr_of));
+                step(rs.lt_at<2>(hi_of(), thr_of));
+                step(rs.lt_at<3>(hi_of(), thr_of));
+                step(rs.lt_at<4>(hi_of(), thr_of));
+                step(rs.lt_at<5>(hi_of(), thr_of));
+                step(rs.lt_at<6>(hi_of(), thr_of));
+                step(rs.lt_at<7>(hi_of(), thr_of));
+                rs.i += 8;
             }
+            for (; t < g.L; t++) step(rs.next_lt(thr_of()));
         }
 #pragma unroll
         for (int k = 0; k < kMaxCat; k++) {

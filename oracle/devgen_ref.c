@@ -8,9 +8,9 @@
  *   - Philox4x32-10 (Salmon et al. 2011; Random123 known answers are checked by the tests);
  *   - base multiset of simulation `sim`: the reference generators of src/trading_models.py:43-128
  *     (three-phase dynamic incl. clipping and tail fill :44-65, Markov-1 :68-85, Markov-2 :87-104,
- *     regime switch :106-128) driven by uniforms u_i = k_i / 2^53, k_i built from words
- *     a = word (i%4) of Philox(key = seed, ctr = (i/4, 0, sim, 0)), b = the same word of ctr = (i/4, 1, sim, 0), combined exactly like NumPy builds a
- *     double from two 32-bit words (a>>5, b>>6); the acceptance tests are the reference's own
+ *     regime switch :106-128) driven by uniforms u_i = k_i / 2^53, k_i = h_i * 2^37 + rest_i with
+ *     h_i = 16-bit half (i%8) of Philox(key = seed, ctr = (i/8, 0, sim, 0)) (word (i%8)/2; upper half for even i, lower for odd i) and
+ *     rest_i = top 37 bits of y0:y1, y = Philox(ctr = (i, 1, sim, 0)); the acceptance tests are the reference's own
  *     (`rand() < p`, choice(): `u < cdf[0]` after cdf normalisation) in floating point;
  *   - shuffle of path (sim, k) (np.random.shuffle of :492).  The run's VALUE LIST is the distinct values in order of first
  *     appearance in the generator's (win, -loss) list, leaving out outcomes the acceptance test can never produce (a segment
@@ -74,14 +74,17 @@ typedef struct {
 
 static double next_uniform(base_stream *s)
 {
-    /* u_i = ((a >> 5) * 2^26 + (b >> 6)) / 2^53, a = word (i%4) of Philox(ctr = (i/4, 0, sim, 0)), b = word (i%4) of
-     * Philox(ctr = (i/4, 1, sim, 0)) */
-    uint32_t ctr_a[4] = {s->i >> 2, 0u, s->sim, 0u}, ctr_b[4] = {s->i >> 2, 1u, s->sim, 0u}, xa[4], xb[4];
+    /* u_i = (h * 2^37 + rest) / 2^53:
+     *   h    = 16-bit half (i%8) of Philox(ctr = (i/8, 0, sim, 0)) -- word (i%8)/2, upper half for even i, lower half for odd i;
+     *   rest = top 37 bits of the 64-bit number y0:y1, y = Philox(ctr = (i, 1, sim, 0)) */
+    uint32_t ctr_a[4] = {s->i >> 3, 0u, s->sim, 0u}, ctr_b[4] = {s->i, 1u, s->sim, 0u}, xa[4], xb[4];
     philox((uint32_t)s->seed, (uint32_t)(s->seed >> 32), ctr_a, xa);
     philox((uint32_t)s->seed, (uint32_t)(s->seed >> 32), ctr_b, xb);
-    uint32_t a = xa[s->i & 3u] >> 5, b = xb[s->i & 3u] >> 6;
+    uint32_t w = xa[(s->i & 7u) >> 1];
+    uint64_t h = (s->i & 1u) ? (w & 0xffffu) : (w >> 16);
+    uint64_t rest = (((uint64_t)xb[0] << 32) | (uint64_t)xb[1]) >> 27;
     s->i++;
-    return (a * 67108864.0 + b) / 9007199254740992.0;
+    return (double)((h << 37) | rest) / 9007199254740992.0;
 }
 
 /* choice([a0, a1], p=[p0, 1-p0]) on the base stream; returns -1 where NumPy raises */

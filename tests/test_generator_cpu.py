@@ -180,24 +180,41 @@ def test_fuzz_generator_and_evaluator_against_the_oracles():
     assert ok > 250 and err >= 5, (ok, err)
 
 
-def test_base_draw_tie_of_the_high_bits_uses_the_second_block():
-    """A Bernoulli draw of the base stream is decided by the top 27 bits of its 53-bit uniform unless they tie with the threshold's
-    (probability 2^-27); only then is the second Philox block generated.  Force the tie: pick the hit rate from the very word the
-    first draw will see, just above and just below the full 53-bit value, and check the outcome against the independent restatement."""
-    seed, sim = 987654321, 17
-    a = harness.philox((seed & 0xffffffff, seed >> 32), (0, 0, sim, 0))[0]
-    b = harness.philox((seed & 0xffffffff, seed >> 32), (0, 1, sim, 0))[0]
+def _draw53(seed, sim, i):
+    """The i-th 53-bit uniform of a simulation's base stream by the published rule, and its 16-bit first look."""
+    key = (seed & 0xffffffff, seed >> 32)
+    w = harness.philox(key, (i >> 3, 0, sim, 0))[(i & 7) >> 1]
+    h = (w & 0xffff) if i & 1 else w >> 16
+    y = harness.philox(key, (i, 1, sim, 0))
+    return (h << 37) | (((y[0] << 32) | y[1]) >> 27), h
+
+
+@pytest.mark.parametrize("draw", [0, 1, 5, 8, 11, 22, 23])
+def test_base_draw_tie_of_the_high_bits_uses_the_second_block(draw):
+    """A Bernoulli draw of the base stream is decided by the 16-bit first look at its 53-bit uniform unless that ties with the
+    threshold's top 16 bits (probability 2^-16); only then is the second Philox block generated.  Force the tie at draw `draw`:
+    take the threshold from the very uniform that draw will see -- equal (no win), one above (win), far above / below with the
+    first look still tied -- and compare the win counts of all three generator loops (segments: whole blocks of eight; Markov-1
+    and Markov-2: per-draw thresholds) with the independent restatement."""
+    seed, sim, L = 987654321, 17, 24
     assert harness.philox((1, 2), (3, 4, 5, 6)) == oracle.devgen_philox((1, 2), (3, 4, 5, 6))
-    k = ((a >> 5) << 26) | (b >> 6)                       # the first uniform as a 53-bit integer
-    for thr, win in ((k + 1, 1), (k, 0), (k + 2 ** 20, 1), (max(k - 2 ** 20, (a >> 5) << 26), 0 if (b >> 6) >= 2 ** 20 else None)):
-        if win is None or thr >> 26 != a >> 5:
-            continue                                      # keep the high bits tied
+    k, h = _draw53(seed, sim, draw)
+    tried = 0
+    for thr in (k, k + 1, k + 2 ** 30, k - 2 ** 30, (h << 37), (h << 37) + 1):
+        if thr >> 37 != h or thr <= 0:
+            continue                                      # keep the first look tied
+        tried += 1
         p = thr / 2.0 ** 53                               # threshold53(p) == thr exactly (thr < 2^53 is representable)
-        prm = make_params(p, 186.0, 219.0, 1, 1, 1, use_markov=True)
-        counts, vals, L = harness.base_counts(prm, seed, sim)
-        assert L == 1 and int(counts[0]) == win, (thr, counts)
-        ref = oracle.devgen_sequences(oracle.make_params(p, 186.0, 219.0, 1, sim + 1, 1, use_markov=True), seed, first_path=sim, n=1)
-        assert (ref[0, 0] == 186.0) == bool(win)
+        for kw in (dict(use_regime=True, regimes=[_regime(L, p, 186.0, 219.0)]),
+                   dict(use_markov=True, p_win_after_win=p, p_win_after_loss=p),
+                   dict(use_markov2=True, p_win_ww=p, p_win_wl=p, p_win_lw=p, p_win_ll=p)):
+            counts, vals, n = harness.base_counts(make_params(p, 186.0, 219.0, L, 1, 1, **kw), seed, sim)
+            ref = oracle.devgen_sequences(oracle.make_params(p, 186.0, 219.0, L, sim + 1, 1, **kw), seed, first_path=sim, n=1)[0]
+            wins = int(sum(c for c, v in zip(counts, vals) if v > 0))
+            assert n == L and wins == int((ref > 0).sum()), (draw, thr, kw, counts)
+            expected = sum(1 for i in range(L) if _draw53(seed, sim, i)[0] < thr)   # every draw sees the same threshold
+            assert wins == expected, (draw, thr, kw)
+    assert tried >= 3
 
 
 def _regime(length, hit, win, loss):

@@ -439,12 +439,12 @@ def main():
                                          rank, world, chunk_paths=ch, device=device)
         return rows, eng.timing()["total_ms"]
 
-    def timed_job(pm, seed, reps):
+    def timed_job(pm, seed, reps, vary_seed=True):
         best = None
         for r in range(reps):
             barrier()
             t0 = time.perf_counter()
-            rows, dev_ms_local = sharded_rows(pm, seed + r)
+            rows, dev_ms_local = sharded_rows(pm, seed + (r if vary_seed else 0))
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
             tt = torch.tensor([wall, dev_ms_local * 1e-3], dtype=torch.float64, device=device)
@@ -464,7 +464,7 @@ def main():
                                     "note": "fixed problem; wall time of the whole sharded call (best of 3), max over ranks"}
         # (d) BASELINE.json config 5 at its stated size: 1e9 paths x 1000 trades x 20 strategies
         pm = make_params(HIT_RATE, AVG_WIN, AVG_LOSS, NUM_TRADES, C5_FULL_SIMS, NUM_SHUFFLES)
-        wall, dev_s, rows = timed_job(pm, 2026, 1)
+        wall, dev_s, rows = timed_job(pm, 2026, 2, vary_seed=False)   # best of 2: a single 1e9-path call is exposed to host hiccups
         extras["c5_full"] = {"paths": C5_FULL_SIMS * NUM_SHUFFLES, "trade_steps": C5_FULL_SIMS * NUM_SHUFFLES * NUM_TRADES * 20, "n_gpus": n_gpus, "wall_s": wall,
                              "value": C5_FULL_SIMS * NUM_SHUFFLES * NUM_TRADES * 20 / wall, "unit": UNIT, "seed": 2026,
                              "avg_profit_strategy1": float(rows[0][0]), "avg_drawdown_strategy1": float(rows[0][1]), "analytic_avg_profit_strategy1": 103063.2,

@@ -38,6 +38,10 @@ extern "C" {
 #define MCTS_NSTRAT 20
 #define MCTS_MAX_REGIMES 16
 #define MCTS_ABI_VERSION 2
+/* Version of the on-device generator's published stream: results of mcts_simulate are a pure function
+ * of (parameters, seed, MCTS_GENERATOR_VERSION) -- independent of chunking, of the number of devices and of the build.  A change
+ * of the stream format (3: eight base draws per Philox block + urn shuffle) bumps it; replay results never depend on it. */
+#define MCTS_GENERATOR_VERSION 3
 
 typedef enum {
     MCTS_OK = 0,
@@ -128,6 +132,7 @@ typedef struct {
 typedef struct mcts_handle mcts_handle;
 
 int mcts_abi_version(void);
+int mcts_generator_version(void);
 const char *mcts_last_error(void);
 
 /* Bind a handle to CUDA device `device` (>= 0). Fails with MCTS_ENODEVICE if the device is

@@ -66,6 +66,7 @@ _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
 PROTOTYPES = [
     ("mcts_abi_version", C.c_int, []),
+    ("mcts_generator_version", C.c_int, []),
     ("mcts_last_error", C.c_char_p, []),
     ("mcts_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     ("mcts_destroy", None, [C.c_void_p]),

@@ -200,6 +200,8 @@ extern "C" {
 
 int mcts_abi_version(void) { return MCTS_ABI_VERSION; }
 
+int mcts_generator_version(void) { return MCTS_GENERATOR_VERSION; }
+
 const char *mcts_last_error(void) { return g_err.c_str(); }
 
 static int mcts_create_impl(int device, mcts_handle **out)

@@ -22,6 +22,7 @@ def test_library_exports_every_symbol_of_the_header():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.mcts_abi_version() == _ffi.ABI_VERSION
+    assert lib.mcts_generator_version() == int(re.search(r"#define MCTS_GENERATOR_VERSION (\d+)", hdr).group(1)) == 3
     assert C.sizeof(_ffi.ChunkResult) == 16 + 6 * 20 * 8 and C.sizeof(_ffi.Agg) == 56
 
 

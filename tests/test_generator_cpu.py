@@ -251,3 +251,26 @@ def test_generator_choice_at_the_value_count_boundaries(name, args, kw):
     for sim in range(args[4]):
         rows = np.sort(out["seqs"][sim * n_sh:(sim + 1) * n_sh], axis=1)
         assert (rows == rows[0]).all(), name
+
+
+def devgen_golden():
+    """tests/golden/devgen_v3.npz as {name: (args, kw, sequences)} (made by tests/golden/make_devgen_golden.py from the plain-C restatement)."""
+    import os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_devgen_golden", os.path.join(sys_path, "make_devgen_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(sys_path, "devgen_v3.npz"))
+    return mod.SEED, {name: (args, kw, z[name + "__values"][z[name + "__codes"]]) for name, args, kw in mod.CASES}
+
+
+def test_generator_stream_known_answers():
+    """The published stream (MCTS_GENERATOR_VERSION 3) is pinned by committed known answers: the device code (g++ build) and the
+    restatement both reproduce every stored sequence.  If this fails after an intended change of the generator, bump the version
+    in include/mcts.h and regenerate the fixture."""
+    seed, cases = devgen_golden()
+    assert len(cases) >= 12
+    for name, (args, kw, gold) in cases.items():
+        assert_bitexact(oracle.devgen_sequences(oracle.make_params(*args, **kw), seed), gold, name + " restatement")
+        assert_bitexact(harness.simulate(make_params(*args, **kw), seed)["seqs"], gold, name + " device code on the CPU")
